@@ -1,0 +1,125 @@
+/*
+ * mvpnet_b200.h — C ABI of the B200-native (sm_100a) MVPNet hot path.
+ *
+ * The reference (maxjaritz/mvpnet) has no C ABI: its lower boundary is six pybind11 torch
+ * extension modules (mvpnet/ops/cuda/*.cpp) taking at::Tensor.  Each entry point below replaces
+ * the at::Tensor-typed function named in its comment with plain device pointers + sizes, so any
+ * host (the torch shim in mvpnet_b200/csrc/torch_ext.cpp, ctypes, or another runtime) can bind it.
+ *
+ * Conventions
+ *   - all data pointers are DEVICE pointers on the current CUDA device; outputs are
+ *     caller-allocated; nothing here allocates or synchronises
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream, which is what the reference's
+ *     `<<<grid, block>>>` launches use)
+ *   - dtype: MVP_F32 or MVP_F64 (the reference dispatches AT_DISPATCH_FLOATING_TYPES)
+ *   - indices are int64 in and out (API-visible dtype of the reference)
+ *   - return value: 0 on success; MVP_ERR_* (<0) for argument errors (the reference raises
+ *     RuntimeError via TORCH_CHECK / CHECK_EQ there); >0 is a cudaError_t from the launch
+ *   - mvp_last_error() returns a thread-local message for the last non-zero return
+ *   - arithmetic contract: squared distances are fma(dz,dz, fma(dy,dy, dx*dx)) with d = key - query
+ *     in the input dtype (what nvcc -O2 emits for the reference loops), comparisons strict
+ */
+#ifndef MVPNET_B200_H_
+#define MVPNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVP_F32 0
+#define MVP_F64 1
+
+#define MVP_ERR_INVALID_ARG (-1)
+#define MVP_ERR_UNSUPPORTED (-2)
+#define MVP_ERR_NULL (-3)
+
+typedef void *mvp_stream_t; /* cudaStream_t */
+
+const char *mvp_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int mvp_abi_version(void);
+
+/* Out-of-range gather/scatter indices (e.g. the -1 rows ball_query emits for a query with no
+ * neighbour) do not fault: forward gathers produce 0, backward scatters skip the element, and a
+ * device-side counter is incremented.  (Reference: device-side assert, group_points_kernel.cu:85,
+ * interpolate_kernel.cu:59,170.)  This call copies the counter to the host (synchronises the
+ * stream) and resets it. */
+int mvp_index_errors_fetch_and_clear(mvp_stream_t stream, uint64_t *count);
+
+/* ---- farthest point sampling ------------------------------------------------------------------
+ * replaces fps_cuda.farthest_point_sample  (mvpnet/ops/cuda/fps.cpp:7-13, fps_kernel.cu:144-180)
+ * points [B,N,D] contiguous, D in {2,3}; index out [B,M] int64; requires 0 < M <= N.
+ * workspace: mvp_fps_workspace_bytes() bytes (may be 0 -> pass NULL). */
+int64_t mvp_fps_workspace_bytes(int64_t B, int64_t N, int64_t D, int64_t M, int dtype);
+int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int64_t M, int dtype,
+            int64_t *index, void *workspace, mvp_stream_t stream);
+
+/* ---- ball query --------------------------------------------------------------------------------
+ * replaces ball_query_cuda.ball_query (ball_query.cpp:7-15, ball_query_kernel.cu:147-187) and,
+ * with distance != NULL, ball_query_distance_cuda.ball_query_distance
+ * (ball_query_distance.cpp:7-15).  query [B,N1,3], key [B,N2,3] contiguous; index [B,N1,K];
+ * distance [B,N1,K] in dtype or NULL.  First K keys in index order with d2 < r*r; tail padded with
+ * the first hit (index only, distance pad = -1); no hit -> row of -1. */
+int mvp_ball_query(const void *query, const void *key, int64_t B, int64_t N1, int64_t N2,
+                   float radius, int64_t K, int dtype, int64_t *index, void *distance,
+                   mvp_stream_t stream);
+
+/* ---- 3-NN --------------------------------------------------------------------------------------
+ * replaces knn_distance_cuda.knn_distance (knn_distance.cpp:8-16, knn_distance_kernel.cu:154-196)
+ * k must be 3 and N2 >= 3.  index [B,N1,3] int64, distance [B,N1,3] squared, ascending, lowest
+ * key index first among equal distances. */
+int mvp_knn_distance(const void *query, const void *key, int64_t B, int64_t N1, int64_t N2,
+                     int64_t k, int dtype, int64_t *index, void *distance, mvp_stream_t stream);
+
+/* ---- group points ------------------------------------------------------------------------------
+ * replaces group_points_cuda.group_points_forward / _backward (group_points.cpp:7-19,
+ * group_points_kernel.cu:25-47, 99-145).
+ * forward: out[b,c,n,k] = in[b,c,index[b,n,k]]; `in` may be strided (element strides sb,sc,sn —
+ * the reference gathers through expand()ed views), index [B,N2,K] and out [B,C,N2,K] contiguous.
+ * backward: grad_in[B,C,N1] (contiguous, fully overwritten) = scatter-add of grad_out. */
+int mvp_group_points_forward(const void *in, int64_t sb, int64_t sc, int64_t sn,
+                             const int64_t *index, int64_t B, int64_t C, int64_t N1, int64_t N2,
+                             int64_t K, int dtype, void *out, mvp_stream_t stream);
+int mvp_group_points_backward(const void *grad_out, const int64_t *index, int64_t B, int64_t C,
+                              int64_t N1, int64_t N2, int64_t K, int dtype, void *grad_in,
+                              mvp_stream_t stream);
+
+/* ---- feature interpolate -----------------------------------------------------------------------
+ * replaces interpolate_cuda.interpolate_forward / _backward (interpolate.cpp:8-22,
+ * interpolate_kernel.cu:78-124, 184-230).  k == 3.
+ * forward: out[b,c,n] = sum_k in[b,c,index[b,n,k]] * weight[b,n,k]; in [B,C,M] with element
+ * strides (sb,sc,sm); index/weight [B,N,3] contiguous; out [B,C,N].
+ * backward: grad_in [B,C,M] (overwritten) = scatter-add of grad_out[b,c,n]*weight[b,n,k]. */
+int mvp_interpolate_forward(const void *in, int64_t sb, int64_t sc, int64_t sm,
+                            const int64_t *index, const void *weight, int64_t B, int64_t C,
+                            int64_t M, int64_t N, int dtype, void *out, mvp_stream_t stream);
+int mvp_interpolate_backward(const void *grad_out, const int64_t *index, const void *weight,
+                             int64_t B, int64_t C, int64_t M, int64_t N, int dtype, void *grad_in,
+                             mvp_stream_t stream);
+
+/* ---- unprojection of depth maps (data side of FeatureAggregation) ------------------------------
+ * replaces depth2xyz + pose + masks, mvpnet/data/scannet_2d3d.py:33-39, 255-262, 273-281.
+ * depth [B,nv,h,w] f32 metres; cam_inv [B,nv,3,3] f32 = inverse intrinsics (np.linalg.inv in the
+ * reference); pose [B,nv,4,4] f32; chunk_box [B,4] f64 {x0,y0,x1,y1} or NULL (margin 0.1 applied
+ * as in the reference).  Outputs (any may be NULL): xyz64 [B,nv*h*w,3] f64 (k-NN input),
+ * xyz32 [B,nv,h,w,3] f32 (`image_xyz`), mask [B,nv*h*w] u8. */
+int mvp_unproject(const float *depth, const float *cam_inv, const float *pose,
+                  const double *chunk_box, int64_t B, int64_t nv, int64_t h, int64_t w,
+                  double *xyz64, float *xyz32, uint8_t *mask, mvp_stream_t stream);
+
+/* ---- 2D->3D k-NN over valid pixels -------------------------------------------------------------
+ * replaces sklearn NearestNeighbors(k,'ball_tree').fit(valid).kneighbors(points) + the remap to
+ * flat pixel ids, mvpnet/data/scannet_2d3d.py:298-313.  query [B,nq,3] f64 (chunk points),
+ * pix_xyz [B,P,3] f64, mask [B,P] u8; index out [B,nq,k] int64 flat pixel ids ascending by
+ * distance, ties -> lowest id; dist2 [B,nq,k] f64 or NULL.  1 <= k <= 8.  A cloud with fewer than
+ * k valid pixels yields -1 in the missing slots (sklearn raises there). */
+int mvp_knn_pixels(const double *query, const double *pix_xyz, const uint8_t *mask, int64_t B,
+                   int64_t nq, int64_t P, int64_t k, int64_t *index, double *dist2,
+                   mvp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVPNET_B200_H_ */

@@ -1,0 +1,267 @@
+// Torch shim over the C ABI (include/mvpnet_b200.h).
+//
+// Exposes, as sub-modules of one extension, the six pybind11 modules the reference builds in
+// mvpnet/ops/setup.py:13-67 with the same function names and argument order
+// (mvpnet/ops/cuda/{fps,ball_query,ball_query_distance,group_points,knn_distance,interpolate}.cpp).
+// The shim only validates (TORCH_CHECK -> RuntimeError like the reference), allocates outputs, takes
+// the CURRENT stream and a device guard (the reference launches on the legacy default stream without
+// a guard; this is stricter and compatible), and forwards raw pointers to the C ABI.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <vector>
+
+#include "../../include/mvpnet_b200.h"
+
+namespace {
+
+inline void check_rc(int rc) { TORCH_CHECK(rc == 0, mvp_last_error(), " (mvpnet_b200 rc=", rc, ")"); }
+
+inline int dtype_of(const at::Tensor &t, const char *name) {
+  if (t.scalar_type() == at::kFloat) return MVP_F32;
+  if (t.scalar_type() == at::kDouble) return MVP_F64;
+  TORCH_CHECK(false, name, " must be float32 or float64, got ", t.scalar_type());
+  return -1;
+}
+
+#define CHECK_CUDA(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
+#define CHECK_CONTIGUOUS(x) TORCH_CHECK((x).is_contiguous(), #x " must be contiguous")
+#define CHECK_INPUT(x) \
+  CHECK_CUDA(x);       \
+  CHECK_CONTIGUOUS(x)
+
+inline mvp_stream_t cur_stream() { return (mvp_stream_t)at::cuda::getCurrentCUDAStream().stream(); }
+
+// fps.cpp:7-13
+at::Tensor farthest_point_sample(const at::Tensor points, const int64_t num_centroids) {
+  CHECK_INPUT(points);
+  TORCH_CHECK(points.dim() == 3, "points must be (B, N, D)");
+  const auto B = points.size(0), N = points.size(1), D = points.size(2);
+  TORCH_CHECK(D == 2 || D == 3, "Only support dim=2 or dim=3");
+  TORCH_CHECK(num_centroids > 0, "Check failed: num_centroids > 0");
+  TORCH_CHECK(N >= num_centroids, "Check failed: num_points >= num_centroids");
+  const int dt = dtype_of(points, "points");
+  c10::cuda::CUDAGuard guard(points.device());
+  auto index = at::empty({B, num_centroids}, points.options().dtype(at::kLong));
+  const int64_t ws = mvp_fps_workspace_bytes(B, N, D, num_centroids, dt);
+  at::Tensor work;
+  if (ws > 0) work = at::empty({ws}, points.options().dtype(at::kByte));
+  check_rc(mvp_fps(points.data_ptr(), B, N, D, num_centroids, dt, index.data_ptr<int64_t>(),
+                   ws > 0 ? work.data_ptr() : nullptr, cur_stream()));
+  return index;
+}
+
+void check_query_key(const at::Tensor &query, const at::Tensor &key) {
+  CHECK_INPUT(query);
+  CHECK_INPUT(key);
+  TORCH_CHECK(query.dim() == 3 && key.dim() == 3, "query/key must be (B, N, 3)");
+  TORCH_CHECK(query.size(2) == 3, "Check failed: query.size(2) == 3");
+  TORCH_CHECK(key.size(2) == 3, "Check failed: key.size(2) == 3");
+  TORCH_CHECK(key.size(0) == query.size(0), "Check failed: key.size(0) == batch_size");
+  TORCH_CHECK(query.scalar_type() == key.scalar_type(), "query and key must have the same dtype");
+  TORCH_CHECK(query.device() == key.device(), "query and key must be on the same device");
+}
+
+// ball_query.cpp:7-15
+at::Tensor ball_query(const at::Tensor query, const at::Tensor key, const float radius, const int64_t max_neighbors) {
+  check_query_key(query, key);
+  TORCH_CHECK(max_neighbors > 0, "max_neighbors must be positive");
+  const int dt = dtype_of(query, "query");
+  c10::cuda::CUDAGuard guard(query.device());
+  auto index = at::empty({query.size(0), query.size(1), max_neighbors}, query.options().dtype(at::kLong));
+  check_rc(mvp_ball_query(query.data_ptr(), key.data_ptr(), query.size(0), query.size(1), key.size(1), radius,
+                          max_neighbors, dt, index.data_ptr<int64_t>(), nullptr, cur_stream()));
+  return index;
+}
+
+// ball_query_distance.cpp:7-15
+std::vector<at::Tensor> ball_query_distance(const at::Tensor query, const at::Tensor key, const float radius,
+                                            const int64_t max_neighbors) {
+  check_query_key(query, key);
+  TORCH_CHECK(max_neighbors > 0, "max_neighbors must be positive");
+  const int dt = dtype_of(query, "query");
+  c10::cuda::CUDAGuard guard(query.device());
+  auto index = at::empty({query.size(0), query.size(1), max_neighbors}, query.options().dtype(at::kLong));
+  auto distance = at::empty({query.size(0), query.size(1), max_neighbors}, query.options());
+  check_rc(mvp_ball_query(query.data_ptr(), key.data_ptr(), query.size(0), query.size(1), key.size(1), radius,
+                          max_neighbors, dt, index.data_ptr<int64_t>(), distance.data_ptr(), cur_stream()));
+  return {index, distance};
+}
+
+// knn_distance.cpp:8-16
+std::vector<at::Tensor> knn_distance(const at::Tensor query, const at::Tensor key, const int64_t k) {
+  check_query_key(query, key);
+  TORCH_CHECK(key.size(1) >= k, "Check failed: num_key >= k");
+  TORCH_CHECK(k == 3, "Only support 3-NN.");
+  const int dt = dtype_of(query, "query");
+  c10::cuda::CUDAGuard guard(query.device());
+  auto index = at::empty({query.size(0), query.size(1), k}, query.options().dtype(at::kLong));
+  auto distance = at::empty({query.size(0), query.size(1), k}, query.options());
+  check_rc(mvp_knn_distance(query.data_ptr(), key.data_ptr(), query.size(0), query.size(1), key.size(1), k, dt,
+                            index.data_ptr<int64_t>(), distance.data_ptr(), cur_stream()));
+  return {index, distance};
+}
+
+// group_points.cpp:7-19
+at::Tensor group_points_forward(const at::Tensor input, const at::Tensor index) {
+  CHECK_CUDA(input);
+  CHECK_CUDA(index);
+  TORCH_CHECK(input.dim() == 3, "Check failed: input.dim() == 3");
+  TORCH_CHECK(index.dim() == 3, "Check failed: index.dim() == 3");
+  TORCH_CHECK(index.size(0) == input.size(0), "Check failed: index.size(0) == batch_size");
+  TORCH_CHECK(index.scalar_type() == at::kLong, "index must be int64");
+  const int dt = dtype_of(input, "input");
+  c10::cuda::CUDAGuard guard(input.device());
+  const auto idx = index.contiguous();
+  const auto B = input.size(0), C = input.size(1), N1 = input.size(2), N2 = idx.size(1), K = idx.size(2);
+  auto out = at::empty({B, C, N2, K}, input.options());
+  check_rc(mvp_group_points_forward(input.data_ptr(), input.stride(0), input.stride(1), input.stride(2),
+                                    idx.data_ptr<int64_t>(), B, C, N1, N2, K, dt, out.data_ptr(), cur_stream()));
+  return out;
+}
+
+at::Tensor group_points_backward(const at::Tensor grad_output, const at::Tensor index, const int64_t num_points) {
+  CHECK_CUDA(grad_output);
+  CHECK_CUDA(index);
+  TORCH_CHECK(grad_output.dim() == 4, "Check failed: grad_output.dim() == 4");
+  TORCH_CHECK(index.dim() == 3, "Check failed: index.dim() == 3");
+  TORCH_CHECK(index.size(0) == grad_output.size(0), "Check failed: index.size(0) == batch_size");
+  TORCH_CHECK(index.size(1) == grad_output.size(2), "Check failed: index.size(1) == num_select");
+  TORCH_CHECK(index.size(2) == grad_output.size(3), "Check failed: index.size(2) == k");
+  TORCH_CHECK(index.scalar_type() == at::kLong, "index must be int64");
+  const int dt = dtype_of(grad_output, "grad_output");
+  c10::cuda::CUDAGuard guard(grad_output.device());
+  const auto g = grad_output.contiguous();
+  const auto idx = index.contiguous();
+  const auto B = g.size(0), C = g.size(1), N2 = g.size(2), K = g.size(3);
+  auto grad_input = at::empty({B, C, num_points}, g.options());
+  check_rc(mvp_group_points_backward(g.data_ptr(), idx.data_ptr<int64_t>(), B, C, num_points, N2, K, dt,
+                                     grad_input.data_ptr(), cur_stream()));
+  return grad_input;
+}
+
+void check_interp(const at::Tensor &x, const at::Tensor &index, const at::Tensor &weight, int64_t num_select) {
+  CHECK_CUDA(x);
+  CHECK_CUDA(index);
+  CHECK_CUDA(weight);
+  TORCH_CHECK(x.dim() == 3 && index.dim() == 3 && weight.dim() == 3, "interpolate: tensors must be 3-D");
+  TORCH_CHECK(index.size(0) == x.size(0), "Check failed: index.size(0) == batch_size");
+  TORCH_CHECK(index.size(2) == 3, "Check failed: k == 3");
+  TORCH_CHECK(index.size(1) == num_select, "Check failed: index.size(1) == num_select");
+  TORCH_CHECK(weight.size(0) == x.size(0), "Check failed: weight.size(0) == batch_size");
+  TORCH_CHECK(weight.size(1) == num_select, "Check failed: weight.size(1) == num_select");
+  TORCH_CHECK(weight.size(2) == 3, "Check failed: weight.size(2) == k");
+  TORCH_CHECK(index.scalar_type() == at::kLong, "index must be int64");
+  TORCH_CHECK(weight.scalar_type() == x.scalar_type(), "weight must have the dtype of the features");
+}
+
+// interpolate.cpp:8-22
+at::Tensor interpolate_forward(const at::Tensor input, const at::Tensor index, const at::Tensor weight) {
+  check_interp(input, index, weight, index.size(1));
+  const int dt = dtype_of(input, "input");
+  c10::cuda::CUDAGuard guard(input.device());
+  const auto idx = index.contiguous();
+  const auto w = weight.contiguous();
+  const auto B = input.size(0), C = input.size(1), M = input.size(2), N = idx.size(1);
+  auto out = at::empty({B, C, N}, input.options());
+  check_rc(mvp_interpolate_forward(input.data_ptr(), input.stride(0), input.stride(1), input.stride(2),
+                                   idx.data_ptr<int64_t>(), w.data_ptr(), B, C, M, N, dt, out.data_ptr(), cur_stream()));
+  return out;
+}
+
+at::Tensor interpolate_backward(const at::Tensor grad_output, const at::Tensor index, const at::Tensor weight,
+                                const int64_t num_inst) {
+  check_interp(grad_output, index, weight, grad_output.size(2));
+  const int dt = dtype_of(grad_output, "grad_output");
+  c10::cuda::CUDAGuard guard(grad_output.device());
+  const auto g = grad_output.contiguous();
+  const auto idx = index.contiguous();
+  const auto w = weight.contiguous();
+  const auto B = g.size(0), C = g.size(1), N = g.size(2);
+  auto grad_input = at::empty({B, C, num_inst}, g.options());
+  check_rc(mvp_interpolate_backward(g.data_ptr(), idx.data_ptr<int64_t>(), w.data_ptr(), B, C, num_inst, N, dt,
+                                    grad_input.data_ptr(), cur_stream()));
+  return grad_input;
+}
+
+// ---- data side of FeatureAggregation (no reference extension; scannet_2d3d.py:33-39,255-313) ----
+std::vector<at::Tensor> unproject(const at::Tensor depth, const at::Tensor cam_inv, const at::Tensor pose,
+                                  const c10::optional<at::Tensor> chunk_box, bool want_xyz64) {
+  CHECK_INPUT(depth);
+  CHECK_INPUT(cam_inv);
+  CHECK_INPUT(pose);
+  TORCH_CHECK(depth.dim() == 4, "depth must be (B, nv, h, w)");
+  const auto B = depth.size(0), nv = depth.size(1), h = depth.size(2), w = depth.size(3);
+  TORCH_CHECK(depth.scalar_type() == at::kFloat && cam_inv.scalar_type() == at::kFloat && pose.scalar_type() == at::kFloat,
+              "depth, cam_inv and pose must be float32");
+  TORCH_CHECK(cam_inv.numel() == B * nv * 9, "cam_inv must be (B, nv, 3, 3)");
+  TORCH_CHECK(pose.numel() == B * nv * 16, "pose must be (B, nv, 4, 4)");
+  const double *box = nullptr;
+  at::Tensor boxc;
+  if (chunk_box.has_value() && chunk_box->defined()) {
+    boxc = chunk_box->contiguous();
+    CHECK_CUDA(boxc);
+    TORCH_CHECK(boxc.scalar_type() == at::kDouble && boxc.numel() == B * 4, "chunk_box must be float64 (B, 4)");
+    box = boxc.data_ptr<double>();
+  }
+  c10::cuda::CUDAGuard guard(depth.device());
+  auto xyz32 = at::empty({B, nv, h, w, 3}, depth.options());
+  auto mask = at::empty({B, nv, h, w}, depth.options().dtype(at::kByte));
+  at::Tensor xyz64;
+  if (want_xyz64) xyz64 = at::empty({B, nv * h * w, 3}, depth.options().dtype(at::kDouble));
+  check_rc(mvp_unproject(depth.data_ptr<float>(), cam_inv.data_ptr<float>(), pose.data_ptr<float>(), box, B, nv, h, w,
+                         want_xyz64 ? xyz64.data_ptr<double>() : nullptr, xyz32.data_ptr<float>(),
+                         mask.data_ptr<uint8_t>(), cur_stream()));
+  return {xyz32, mask, want_xyz64 ? xyz64 : at::Tensor()};
+}
+
+std::vector<at::Tensor> knn_pixels(const at::Tensor query, const at::Tensor pix_xyz, const at::Tensor mask, int64_t k) {
+  CHECK_INPUT(query);
+  CHECK_INPUT(pix_xyz);
+  CHECK_INPUT(mask);
+  TORCH_CHECK(query.dim() == 3 && query.size(2) == 3, "query must be (B, nq, 3)");
+  TORCH_CHECK(pix_xyz.dim() == 3 && pix_xyz.size(2) == 3, "pix_xyz must be (B, P, 3)");
+  TORCH_CHECK(query.scalar_type() == at::kDouble && pix_xyz.scalar_type() == at::kDouble, "query/pix_xyz must be float64");
+  TORCH_CHECK(mask.scalar_type() == at::kByte || mask.scalar_type() == at::kBool, "mask must be uint8/bool");
+  TORCH_CHECK(mask.numel() == pix_xyz.size(0) * pix_xyz.size(1), "mask must be (B, P)");
+  TORCH_CHECK(query.size(0) == pix_xyz.size(0), "batch mismatch");
+  c10::cuda::CUDAGuard guard(query.device());
+  auto index = at::empty({query.size(0), query.size(1), k}, query.options().dtype(at::kLong));
+  auto dist2 = at::empty({query.size(0), query.size(1), k}, query.options());
+  check_rc(mvp_knn_pixels(query.data_ptr<double>(), pix_xyz.data_ptr<double>(), (const uint8_t *)mask.data_ptr(),
+                          query.size(0), query.size(1), pix_xyz.size(1), k, index.data_ptr<int64_t>(),
+                          dist2.data_ptr<double>(), cur_stream()));
+  return {index, dist2};
+}
+
+int64_t index_errors_fetch_and_clear() {
+  uint64_t n = 0;
+  check_rc(mvp_index_errors_fetch_and_clear(cur_stream(), &n));
+  return (int64_t)n;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "mvpnet_b200: sm_100a kernels behind the mvpnet.ops extension interface";
+  m.def("abi_version", &mvp_abi_version);
+  m.def("index_errors_fetch_and_clear", &index_errors_fetch_and_clear);
+  auto fps = m.def_submodule("fps_cuda");
+  fps.def("farthest_point_sample", &farthest_point_sample, "Farthest point sampling (CUDA)");
+  auto bq = m.def_submodule("ball_query_cuda");
+  bq.def("ball_query", &ball_query, "Ball query (CUDA)");
+  auto bqd = m.def_submodule("ball_query_distance_cuda");
+  bqd.def("ball_query_distance", &ball_query_distance, "Ball query with distance (CUDA)");
+  auto gp = m.def_submodule("group_points_cuda");
+  gp.def("group_points_forward", &group_points_forward, "Group points forward (CUDA)");
+  gp.def("group_points_backward", &group_points_backward, "Group points backward (CUDA)");
+  auto knn = m.def_submodule("knn_distance_cuda");
+  knn.def("knn_distance", &knn_distance, "k-nearest neighbor with distance (CUDA)");
+  auto ip = m.def_submodule("interpolate_cuda");
+  ip.def("interpolate_forward", &interpolate_forward, "Interpolate feature forward (CUDA)");
+  ip.def("interpolate_backward", &interpolate_backward, "Interpolate feature backward (CUDA)");
+  auto ds = m.def_submodule("unproject_cuda");
+  ds.def("unproject", &unproject, "Depth unprojection (CUDA)");
+  ds.def("knn_pixels", &knn_pixels, "2D->3D k-NN over valid pixels (CUDA)");
+}

@@ -1,0 +1,23 @@
+"""group_points — mirrors mvpnet/ops/group_points.py:5-31."""
+import torch
+
+from ._util import ext
+
+
+class GroupPointsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, index):
+        ctx.save_for_backward(index)
+        ctx.num_points = points.size(2)
+        return ext().group_points_cuda.group_points_forward(points, index)
+
+    @staticmethod
+    def backward(ctx, *grad_output):
+        (index,) = ctx.saved_tensors
+        grad = ext().group_points_cuda.group_points_backward(grad_output[0], index, ctx.num_points)
+        return grad, None
+
+
+def group_points(points, index):
+    """points (B, C, N1), index int64 (B, N2, K) -> (B, C, N2, K) with out[b,c,n,k] = points[b,c,index[b,n,k]]."""
+    return GroupPointsFunction.apply(points, index)

@@ -1,0 +1,23 @@
+"""feature_interpolate — mirrors mvpnet/ops/interpolate.py:5-34."""
+import torch
+
+from ._util import ext
+
+
+class FeatureInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feature, index, weight):
+        ctx.save_for_backward(index, weight)
+        ctx.n = feature.size(2)
+        return ext().interpolate_cuda.interpolate_forward(feature, index, weight)
+
+    @staticmethod
+    def backward(ctx, *grad_out):
+        index, weight = ctx.saved_tensors
+        grad = ext().interpolate_cuda.interpolate_backward(grad_out[0], index, weight, ctx.n)
+        return grad, None, None
+
+
+def feature_interpolate(feature, index, weight):
+    """feature (B, C, N1), index int64 (B, N2, 3), weight (B, N2, 3) -> (B, C, N2)."""
+    return FeatureInterpolate.apply(feature, index, weight)

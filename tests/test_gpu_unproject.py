@@ -1,0 +1,77 @@
+"""GPU parity for the data side of FeatureAggregation: depth unprojection and the 2D->3D k-NN
+against the CPU oracle (bit-exact: fp64 arithmetic with a fixed operation order, integer ids)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make_views(b, nv, h, w, seed):
+    rng = np.random.RandomState(seed)
+    depth = rng.uniform(0.5, 4.0, (b, nv, h, w)).astype(np.float32)
+    depth[rng.rand(b, nv, h, w) < 0.1] = 0.0
+    cam = np.array([[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]], np.float32)
+    cam[0] /= 4
+    cam[1] /= 4
+    cam_inv = np.broadcast_to(np.linalg.inv(cam), (b, nv, 3, 3)).copy()
+    pose = np.zeros((b, nv, 4, 4), np.float32)
+    for i in range(b):
+        for f in range(nv):
+            q, _ = np.linalg.qr(rng.randn(3, 3))
+            if np.linalg.det(q) < 0:
+                q[:, 0] = -q[:, 0]
+            pose[i, f, :3, :3] = q
+            pose[i, f, :3, 3] = rng.uniform(-1, 1, 3)
+            pose[i, f, 3, 3] = 1
+    return depth, cam_inv, pose
+
+
+@pytest.mark.parametrize('b,nv,h,w,box', [(1, 1, 120, 160, False), (2, 5, 120, 160, True), (1, 3, 17, 23, True)])
+def test_unproject(b, nv, h, w, box):
+    import mvpnet_b200
+    ext = mvpnet_b200.load_ext()
+    depth, cam_inv, pose = make_views(b, nv, h, w, 0)
+    boxes = np.array([[-0.5, -0.5, 1.0, 1.0]] * b, np.float64) if box else None
+    t = lambda a: torch.from_numpy(a).cuda()
+    xyz32, mask, xyz64 = ext.unproject_cuda.unproject(t(depth), t(cam_inv), t(pose), t(boxes) if box else None, True)
+    for i in range(b):
+        w64, w32, wm = oracle.unproject(depth[i], cam_inv[i], pose[i], boxes[i] if box else None)
+        assert np.array_equal(xyz64[i].cpu().numpy().reshape(nv, h, w, 3), w64)
+        assert np.array_equal(xyz32[i].cpu().numpy(), w32)
+        assert np.array_equal(mask[i].cpu().numpy().astype(bool), wm)
+
+
+@pytest.mark.parametrize('nq,nv,k', [(2048, 1, 3), (1024, 5, 3), (257, 2, 1), (300, 2, 8)])
+def test_knn_pixels(nq, nv, k):
+    import mvpnet_b200
+    ext = mvpnet_b200.load_ext()
+    b, h, w = 2, 120, 160
+    depth, cam_inv, pose = make_views(b, nv, h, w, 1)
+    rng = np.random.RandomState(2)
+    qs, idxs, d2s = [], [], []
+    pix, msk = [], []
+    for i in range(b):
+        x64, _, m = oracle.unproject(depth[i], cam_inv[i], pose[i])
+        flat = x64.reshape(-1, 3)
+        valid = np.nonzero(m.reshape(-1))[0]
+        q = flat[rng.choice(valid, nq)] + rng.randn(nq, 3) * 0.02
+        q = q.astype(np.float32).astype(np.float64)   # chunk points are float32 in the reference
+        ii, dd = oracle.knn_pixels(q, flat, m, k)
+        qs.append(q); idxs.append(ii); d2s.append(dd); pix.append(flat); msk.append(m.reshape(-1))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    gi, gd = ext.unproject_cuda.knn_pixels(t(np.stack(qs)), t(np.stack(pix)), t(np.stack(msk).astype(np.uint8)), k)
+    assert np.array_equal(gi.cpu().numpy(), np.stack(idxs))
+    assert np.array_equal(gd.cpu().numpy(), np.stack(d2s))
+
+
+def test_knn_pixels_too_few_valid():
+    import mvpnet_b200
+    ext = mvpnet_b200.load_ext()
+    pix = torch.zeros(1, 10, 3, dtype=torch.float64).cuda()
+    mask = torch.zeros(1, 10, dtype=torch.uint8).cuda()
+    mask[0, 4] = 1
+    gi, _ = ext.unproject_cuda.knn_pixels(torch.ones(1, 2, 3, dtype=torch.float64).cuda(), pix, mask, 3)
+    assert gi.cpu().numpy().tolist() == [[[4, -1, -1], [4, -1, -1]]]
