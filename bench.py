@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — chunks/sec of the MVPNet forward (8192 pts, 5 views 160x120) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of synthetic chunks per GPU (BASELINE config 4's
+per-rank shard: 32 chunks x 8192 points x 5 views of 160x120): depth unprojection + 2D->3D 3-NN,
+UNet-ResNet34 on the views, FeatureAggregation, PN2SSG, and (N > 1) one NCCL all-gather of the logits.
+
+  value  chunks/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e    chunks/s through the public API from pinned HOST buffers: H2D of the step's inputs and the
+         D2H read of its logits are inside the timed region
+  roofline      the dominant kernel of this package inside the step, timed live with CUDA events
+  cpu_baseline  the same forward on the host CPU cores (PyTorch CPU modules of the same architecture +
+                the C oracle for the six extension ops + numpy/scikit-learn for unprojection / k-NN, as the
+                reference's DataLoader workers do), on a bounded sample
+
+--impl reference runs only that CPU arm (the reference has no CPU implementation of its CUDA ops and
+its sources cannot travel to the GPU box; kind = "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_POINTS, NUM_VIEWS, H, W, NUM_CLASSES, KNN = 8192, 5, 120, 160, 20, 3
+METRIC = 'chunks/sec MVPNet fwd (8192 pts, 5 views 160x120)'
+
+
+# ------------------------------------------------------------------------------------------------
+def build_model(device):
+    from mvpnet_b200 import synthetic
+    from mvpnet_b200.modules import MVPNet3D, PN2SSG
+    from mvpnet_b200.unet import UNetResNet34
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        net2d = UNetResNet34(NUM_CLASSES, p=0.5, pretrained=False)
+    model = MVPNet3D(net2d, None, PN2SSG(64, NUM_CLASSES), in_channels=64, mlp_channels=(64, 64, 64),
+                     reduction='sum', use_relation=True)
+    synthetic.fill_parameters(model, seed=6)
+    return model.eval().to(device)
+
+
+def make_host_batch(seeds, pin):
+    from mvpnet_b200 import synthetic
+    from mvpnet_b200.data import invert_intrinsics
+    chunks = [synthetic.make_chunk(seed=s, num_points=NUM_POINTS, num_views=NUM_VIEWS, h=H, w=W) for s in seeds]
+    host = {
+        'images': torch.from_numpy(np.stack([c['images'] for c in chunks])),
+        'depth': torch.from_numpy(np.stack([c['depth'] for c in chunks])),
+        'pose': torch.from_numpy(np.stack([c['pose'] for c in chunks])),
+        'cam_inv': torch.from_numpy(np.stack([np.broadcast_to(invert_intrinsics(c['cam_matrix']), (NUM_VIEWS, 3, 3)) for c in chunks]).copy()),
+        'points': torch.from_numpy(np.stack([c['points'] for c in chunks])),          # (b, np, 3)
+        'chunk_box': torch.from_numpy(np.stack([c['chunk_box'] for c in chunks])),
+    }
+    if pin:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    return host, chunks
+
+
+def hot_path(model, dev, strict_overlap=True):
+    """One step on device-resident inputs: returns seg_logit (b, 20, np)."""
+    from mvpnet_b200.data import unproject_and_knn
+    rg = unproject_and_knn(dev['depth'], None, dev['pose'], dev['points'], k=KNN, chunk_box=dev['chunk_box'],
+                           cam_inv=dev['cam_inv'])
+    batch = {'images': dev['images'], 'image_xyz': rg['image_xyz'], 'knn_indices': rg['knn_indices'],
+             'points': dev['points_cm']}
+    return model.fast_forward(batch)['seg_logit']
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if self.rows[0][1].replace('.', '').isdigit() else None,
+                'samples': len(self.rows), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes / work per launch of each kernel, per chunk
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_chunk():
+    P = NUM_VIEWS * H * W
+    n = [8192, 2048, 512, 128, 32]
+    c_sa_in = [64, 64, 128, 256]
+    c_sa_out = [64, 128, 256, 512]
+    out = {
+        'unproject': P * 4 + P * (12 + 24 + 1),
+        'knn_pixels': P * 25 + NUM_POINTS * 24 + NUM_POINTS * KNN * 16,
+        'feature_aggregation': NUM_POINTS * KNN * (64 * 4 + 12 + 8) + NUM_POINTS * 12 + NUM_POINTS * 64 * 4,
+    }
+    for i in range(4):
+        N, M = n[i], n[i + 1]
+        out['fps%d' % (i + 1)] = N * 12 + M * 8
+        out['ball_query%d' % (i + 1)] = M * 12 + N * 12 + M * 32 * 8
+        out['set_abstraction%d' % (i + 1)] = N * c_sa_in[i] * 4 + N * 12 + M * 32 * 8 + M * 12 + M * c_sa_out[i] * 4
+    fp_cs, fp_cd, fp_out = [512, 256, 256, 128], [256, 128, 64, 0], [256, 256, 128, NUM_CLASSES]
+    for i in range(4):
+        Ns, Nd = n[4 - i], n[3 - i]
+        out['knn_distance%d' % (i + 1)] = Nd * 12 + Ns * 12 + Nd * 3 * 12
+        out['feature_propagation%d' % (i + 1)] = Ns * fp_cs[i] * 4 + Nd * 36 + Nd * fp_cd[i] * 4 + Nd * fp_out[i] * 4
+    return out
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p['hbm_gbs'], 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: reference architecture on the host cores
+# ------------------------------------------------------------------------------------------------
+class _OracleExt:
+    """Stands in for the CUDA extension so that mvpnet_b200.modules runs on CPU tensors — used ONLY by the
+    cpu_baseline / --impl reference legs of this benchmark."""
+
+    def __init__(self):
+        import oracle
+        for k, v in oracle.ext_modules().items():
+            setattr(self, k, v)
+
+
+def cpu_forward_factory():
+    import oracle
+    from sklearn.neighbors import NearestNeighbors
+    import mvpnet_b200.ops._util as util
+    util.ext = _OracleExt().__class__  # placeholder replaced below
+    inst = _OracleExt()
+    util.ext = lambda: inst
+    for mod in ('fps', 'ball_query', 'group_points', 'knn_distance', 'interpolate'):
+        m = __import__('mvpnet_b200.ops.' + mod, fromlist=['ext'])
+        m.ext = util.ext
+    model = build_model('cpu')
+
+    def run(chunk):
+        # data side exactly as scannet_2d3d.py:255-313: numpy unprojection (oracle restatement) + sklearn ball tree
+        ci = np.linalg.inv(chunk['cam_matrix'][:3, :3])
+        xyz64, xyz32, mask = oracle.unproject(chunk['depth'], ci, chunk['pose'], chunk['chunk_box'])
+        valid = np.nonzero(mask.reshape(-1))[0]
+        nbrs = NearestNeighbors(n_neighbors=KNN, algorithm='ball_tree').fit(xyz64.reshape(-1, 3)[valid])
+        _, knn = nbrs.kneighbors(chunk['points'])
+        knn = valid[knn]
+        batch = {'images': torch.from_numpy(chunk['images'])[None], 'image_xyz': torch.from_numpy(xyz32)[None],
+                 'knn_indices': torch.from_numpy(knn.astype(np.int64))[None],
+                 'points': torch.from_numpy(np.ascontiguousarray(chunk['points'].T))[None]}
+        with torch.no_grad():
+            return model(batch)['seg_logit']
+    return run
+
+
+def cpu_arm(steps, warmup, chunks_per_step=1):
+    from mvpnet_b200 import synthetic
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    run = cpu_forward_factory()
+    chunks = [synthetic.make_chunk(seed=1000 + i) for i in range(chunks_per_step)]
+    for _ in range(warmup):
+        run(chunks[0])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for c in chunks:
+            run(c)
+    dt = time.perf_counter() - t0
+    n = steps * chunks_per_step
+    return {'value': n / dt, 'unit': 'chunks/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d chunk forward(s) of the same workload (8192 pts, 5 views) on %d host threads: PyTorch CPU modules + C oracle ops + sklearn ball-tree k-NN' % (n, cores),
+            'ms_per_chunk': dt / n * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--chunks-per-gpu', type=int, default=32)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--tf32-2d', action='store_true', help='allow TF32 in the cuDNN 2D network (breaks the 1e-4 logit parity; reported in config)')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    config = {'workload': 'BASELINE config 3/4: full MVPNet forward, %d chunks per GPU per step (8192 pts, 5 views 160x120), '
+                          'unproject + 2D->3D 3-NN + UNetResNet34 + FeatureAggregation + PN2SSG%s' %
+                          (args.chunks_per_gpu, ' + NCCL all-gather of logits' if world > 1 else ''),
+              'chunks_per_gpu': args.chunks_per_gpu, 'global_chunks': args.chunks_per_gpu * world,
+              'parallelism': 'chunk-sharded x%d, replicated weights' % world,
+              'l2_policy': 'no flush: per-step working set (~0.8 GB of images/feature maps per GPU) exceeds the 126 MB L2',
+              'net_2d_math': 'tf32' if args.tf32_2d else 'fp32 (cuDNN, TF32 off)'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        res = cpu_arm(max(args.steps, 1), max(args.warmup, 1) if args.warmup else 0)
+        line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'chunks/s', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_per_chunk'], 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': res, 'e2e': {'value': res['value'], 'unit': 'chunks/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=device)
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32_2d)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    import mvpnet_b200
+    mvpnet_b200.load_ext()
+    from mvpnet_b200 import engine
+
+    model = build_model(device)
+    model.net_2d.to(memory_format=torch.channels_last)
+    cpg = args.chunks_per_gpu
+    host, _ = make_host_batch([rank * cpg + i for i in range(cpg)], pin=True)
+
+    def to_device(h):
+        d = {k: v.to(device, non_blocking=True) for k, v in h.items()}
+        d['images'] = d['images']
+        d['points_cm'] = d['points'].transpose(1, 2).contiguous()     # (b, 3, np): the reference's `points`
+        return d
+
+    gathered = torch.empty(world * cpg, NUM_CLASSES, NUM_POINTS, device=device) if world > 1 else None
+    host_out = torch.empty(cpg, NUM_CLASSES, NUM_POINTS).pin_memory()
+
+    def step_device(dev):
+        with torch.no_grad():
+            logit = hot_path(model, dev)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, logit)
+        return logit
+
+    def step_e2e():
+        dev = to_device(host)
+        logit = step_device(dev)
+        host_out.copy_(logit, non_blocking=True)
+        return logit
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    dev = to_device(host)
+    for _ in range(warmup):
+        step_device(dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(lambda: step_device(dev), args.steps)
+    clocks = sampler.summary() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-stage device time of this package's kernels (events on the launching stream), no overlap
+    stage_ms = {}
+    with torch.no_grad(), engine.profile() as prof:
+        for _ in range(max(3, min(args.steps, 5))):
+            from mvpnet_b200.data import unproject_and_knn
+            rg = unproject_and_knn(dev['depth'], None, dev['pose'], dev['points'], k=KNN, chunk_box=dev['chunk_box'], cam_inv=dev['cam_inv'])
+            batch = {'images': dev['images'], 'image_xyz': rg['image_xyz'], 'knn_indices': rg['knn_indices'], 'points': dev['points_cm']}
+            model.fast_forward(batch, overlap=False)
+        for k, v in prof.summary().items():
+            stage_ms[k] = float(np.median(v))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    chunks = cpg * world * args.steps
+    value = chunks / (ms_total / 1e3)
+    e2e_value = chunks / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = host_out.numel() * host_out.element_size()
+    bytes_pc = algorithmic_bytes_per_chunk()
+    peak, peak_src = peaks()
+    mine = {k: v for k, v in stage_ms.items() if k != 'net_2d'}
+    top = max(mine, key=mine.get)
+    achieved = bytes_pc[top] * cpg / (mine[top] / 1e3) / 1e9
+    stages = {k: {'ms': round(v, 4), 'alg_MB': round(bytes_pc.get(k, 0) * cpg / 1e6, 3),
+                  'GBps': round(bytes_pc.get(k, 0) * cpg / (v / 1e3) / 1e9, 1) if k in bytes_pc else None}
+              for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
+    line = {'metric': METRIC, 'value': value, 'unit': 'chunks/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'chunks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': 23 * args.steps,
+            'roofline': {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src, 'ms_per_launch': mine[top],
+                         'note': 'algorithmic bytes per launch = per-chunk bytes (SURVEY 8d) x %d chunks' % cpg},
+            'stages': stages,
+            'hot_path_ms_per_step_excl_net2d': sum(mine.values())}
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'] = cpu_arm(steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

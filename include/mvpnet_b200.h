@@ -119,6 +119,57 @@ int mvp_knn_pixels(const double *query, const double *pix_xyz, const uint8_t *ma
                    int64_t nq, int64_t P, int64_t k, int64_t *index, double *dist2,
                    mvp_stream_t stream);
 
+
+/* ==== fused inference kernels (fp32) =============================================================
+ * Layout between fused kernels is POINT-MAJOR: features [B, N, C] with one point's channels
+ * contiguous (the reference's public tensors are channel-major [B, C, N]; the host transposes at the
+ * two ends of the fast path only).
+ *
+ * mvp_mlp_chain_t: a SharedMLP with eval-mode BatchNorm folded in (common/nn/modules/mlp.py:38-75,
+ * conv.py:29-51): layer l computes act(bias[l] + x . wt[l]) with wt[l] stored k-major [cin[l]][cout[l]],
+ * zero padded; cin[0] is the (padded, multiple of 4) width of the built input row, cout[l] multiples
+ * of 8, cin[l+1] == cout[l]; out_channels = true width of the last layer. */
+#define MVP_MLP_MAX_LAYERS 6
+typedef struct {
+  int32_t num_layers;
+  int32_t cin[MVP_MLP_MAX_LAYERS];
+  int32_t cout[MVP_MLP_MAX_LAYERS];
+  int32_t relu[MVP_MLP_MAX_LAYERS];
+  const float *wt[MVP_MLP_MAX_LAYERS];
+  const float *bias[MVP_MLP_MAX_LAYERS];
+  int32_t out_channels;
+} mvp_mlp_chain_t;
+
+/* replaces QueryGrouper.forward + SharedMLP(ndim=2) + torch.max(dim=3) of SetAbstraction
+ * (mvpnet/models/pn2/modules.py:20-37, 106-108) given the ball_query index:
+ * row(b,m,k) = cat[feat[b,nbr[b,m,k],:], xyz[b,nbr[b,m,k],:] - new_xyz[b,m,:]]  (features first),
+ * out[b,m,:] = max_k MLP(row).  feat [B,N,C] or NULL (C = 0), xyz [B,N,3], new_xyz [B,M,3],
+ * nbr [B,M,K] int64 with K == 32, out [B,M,out_channels].  chain->cin[0] >= C + 3. */
+int mvp_fused_set_abstraction(const float *feat, int64_t C, const float *xyz, const float *new_xyz,
+                              const int64_t *nbr, int64_t B, int64_t N, int64_t M, int64_t K,
+                              const mvp_mlp_chain_t *chain, float *out, mvp_stream_t stream);
+
+/* replaces the two group_points of MVPNet3D.forward + FeatureAggregation.forward
+ * (mvpnet/models/mvpnet_3d.py:100-109, 37-61): for point p and neighbour pixel j = knn[b,p,i]:
+ * row = cat[feat2d[b, j, :], d = pix_xyz[b,j,:] - points[b,p,:], |d|^2]; out[b,p,:] = sum_i|max_i MLP(row).
+ * feat2d is the 2D network output addressed in place: element (b, view, c, y, x) at
+ * feat2d[(b*nv+view)*s_n + c*s_c + y*s_h + x*s_w] (NCHW or channels-last); pix_xyz [B,nv*h*w,3];
+ * points [B,Np,3]; knn [B,Np,K] flat pixel ids, 1 <= K <= 4; out [B,Np,out_channels]. */
+int mvp_fused_feature_aggregation(const float *feat2d, int64_t s_n, int64_t s_c, int64_t s_h, int64_t s_w,
+                                  int64_t C, int64_t nv, int64_t h, int64_t w, const float *pix_xyz,
+                                  const float *points, const int64_t *knn, int64_t B, int64_t Np, int64_t K,
+                                  int reduce_sum, const mvp_mlp_chain_t *chain, float *out,
+                                  mvp_stream_t stream);
+
+/* replaces FeatureInterpolator.forward + SharedMLP(ndim=1) of FeaturePropagation
+ * (mvpnet/models/pn2/modules.py:122-149, 178-186), optionally followed by the segmentation head
+ * (pn2ssg.py:112-115) as extra chain layers, given the 3-NN (index, squared distance):
+ * w_k = (1/max(d_k,eps)) / sum_k(1/max(d_k,eps)); row = cat[sum_k w_k * sparse[b,idx_k,:], skip[b,n,:]].
+ * sparse_feat [B,Ns,Cs], idx/dist2 [B,Nd,3], skip [B,Nd,Cd] or NULL, out [B,Nd,out_channels]. */
+int mvp_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const int64_t *idx, const float *dist2,
+                                  const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
+                                  const mvp_mlp_chain_t *chain, float *out, mvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

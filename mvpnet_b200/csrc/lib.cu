@@ -8,3 +8,4 @@
 #include "interpolate.cu"
 #include "unproject.cu"
 #include "knn_pixels.cu"
+#include "fused_mlp.cu"

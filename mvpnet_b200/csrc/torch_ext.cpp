@@ -235,6 +235,109 @@ std::vector<at::Tensor> knn_pixels(const at::Tensor query, const at::Tensor pix_
   return {index, dist2};
 }
 
+
+// ---- fused inference kernels (point-major layout; see include/mvpnet_b200.h) ----------------------
+struct Chain {
+  mvp_mlp_chain_t c;
+  Chain(const std::vector<at::Tensor> &wts, const std::vector<at::Tensor> &biases, const std::vector<int64_t> &relu,
+        int64_t out_channels, const at::Device &dev) {
+    TORCH_CHECK(!wts.empty() && wts.size() <= MVP_MLP_MAX_LAYERS, "fused mlp: 1..", MVP_MLP_MAX_LAYERS, " layers");
+    TORCH_CHECK(wts.size() == biases.size() && wts.size() == relu.size(), "fused mlp: list lengths differ");
+    c.num_layers = (int32_t)wts.size();
+    c.out_channels = (int32_t)out_channels;
+    for (size_t l = 0; l < wts.size(); ++l) {
+      const auto &w = wts[l];
+      const auto &b = biases[l];
+      TORCH_CHECK(w.is_cuda() && b.is_cuda() && w.device() == dev && b.device() == dev, "fused mlp: weights on wrong device");
+      TORCH_CHECK(w.is_contiguous() && b.is_contiguous() && w.dim() == 2 && b.dim() == 1, "fused mlp: weights must be contiguous [cin][cout] / [cout]");
+      TORCH_CHECK(w.scalar_type() == at::kFloat && b.scalar_type() == at::kFloat, "fused mlp: weights must be float32");
+      TORCH_CHECK(b.size(0) == w.size(1), "fused mlp: bias/weight mismatch");
+      c.cin[l] = (int32_t)w.size(0);
+      c.cout[l] = (int32_t)w.size(1);
+      c.relu[l] = (int32_t)relu[l];
+      c.wt[l] = w.data_ptr<float>();
+      c.bias[l] = b.data_ptr<float>();
+    }
+  }
+};
+
+#define CHECK_F32(x) TORCH_CHECK((x).scalar_type() == at::kFloat, #x " must be float32")
+
+at::Tensor fused_set_abstraction(const c10::optional<at::Tensor> feat, const at::Tensor xyz, const at::Tensor new_xyz,
+                                 const at::Tensor nbr, const std::vector<at::Tensor> wts, const std::vector<at::Tensor> biases,
+                                 const std::vector<int64_t> relu, int64_t out_channels) {
+  CHECK_INPUT(xyz); CHECK_INPUT(new_xyz); CHECK_INPUT(nbr);
+  CHECK_F32(xyz); CHECK_F32(new_xyz);
+  TORCH_CHECK(xyz.dim() == 3 && xyz.size(2) == 3 && new_xyz.dim() == 3 && new_xyz.size(2) == 3, "xyz/new_xyz must be (B, N, 3)");
+  TORCH_CHECK(nbr.scalar_type() == at::kLong && nbr.dim() == 3, "nbr must be int64 (B, M, K)");
+  const auto B = xyz.size(0), N = xyz.size(1), M = new_xyz.size(1), K = nbr.size(2);
+  TORCH_CHECK(new_xyz.size(0) == B && nbr.size(0) == B && nbr.size(1) == M, "fused_set_abstraction: shape mismatch");
+  int64_t C = 0;
+  const float *fp = nullptr;
+  if (feat.has_value() && feat->defined()) {
+    CHECK_INPUT((*feat)); CHECK_F32((*feat));
+    TORCH_CHECK(feat->dim() == 3 && feat->size(0) == B && feat->size(1) == N, "feat must be (B, N, C)");
+    C = feat->size(2);
+    fp = feat->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(xyz.device());
+  Chain ch(wts, biases, relu, out_channels, xyz.device());
+  auto out = at::empty({B, M, out_channels}, xyz.options());
+  check_rc(mvp_fused_set_abstraction(fp, C, xyz.data_ptr<float>(), new_xyz.data_ptr<float>(), nbr.data_ptr<int64_t>(), B, N, M,
+                                     K, &ch.c, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
+at::Tensor fused_feature_aggregation(const at::Tensor feat2d, const at::Tensor pix_xyz, const at::Tensor points,
+                                     const at::Tensor knn, bool reduce_sum, const std::vector<at::Tensor> wts,
+                                     const std::vector<at::Tensor> biases, const std::vector<int64_t> relu, int64_t out_channels) {
+  CHECK_CUDA(feat2d); CHECK_F32(feat2d);
+  CHECK_INPUT(pix_xyz); CHECK_INPUT(points); CHECK_INPUT(knn);
+  CHECK_F32(pix_xyz); CHECK_F32(points);
+  TORCH_CHECK(feat2d.dim() == 5, "feat2d must be (B, nv, C, h, w) (any strides with a uniform view stride)");
+  const auto B = feat2d.size(0), nv = feat2d.size(1), C = feat2d.size(2), h = feat2d.size(3), w = feat2d.size(4);
+  TORCH_CHECK(feat2d.stride(0) == nv * feat2d.stride(1), "feat2d: batch and view axes must be collapsible");
+  TORCH_CHECK(pix_xyz.dim() == 3 && pix_xyz.size(0) == B && pix_xyz.size(1) == nv * h * w && pix_xyz.size(2) == 3,
+              "pix_xyz must be (B, nv*h*w, 3)");
+  TORCH_CHECK(points.dim() == 3 && points.size(0) == B && points.size(2) == 3, "points must be (B, Np, 3)");
+  TORCH_CHECK(knn.scalar_type() == at::kLong && knn.dim() == 3 && knn.size(0) == B && knn.size(1) == points.size(1),
+              "knn must be int64 (B, Np, K)");
+  c10::cuda::CUDAGuard guard(feat2d.device());
+  Chain ch(wts, biases, relu, out_channels, feat2d.device());
+  auto out = at::empty({B, points.size(1), out_channels}, points.options());
+  check_rc(mvp_fused_feature_aggregation(feat2d.data_ptr<float>(), feat2d.stride(1), feat2d.stride(2), feat2d.stride(3),
+                                         feat2d.stride(4), C, nv, h, w, pix_xyz.data_ptr<float>(), points.data_ptr<float>(),
+                                         knn.data_ptr<int64_t>(), B, points.size(1), knn.size(2), reduce_sum ? 1 : 0, &ch.c,
+                                         out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
+at::Tensor fused_feature_propagation(const at::Tensor sparse_feat, const at::Tensor idx, const at::Tensor dist2,
+                                     const c10::optional<at::Tensor> skip, double eps, const std::vector<at::Tensor> wts,
+                                     const std::vector<at::Tensor> biases, const std::vector<int64_t> relu, int64_t out_channels) {
+  CHECK_INPUT(sparse_feat); CHECK_INPUT(idx); CHECK_INPUT(dist2);
+  CHECK_F32(sparse_feat); CHECK_F32(dist2);
+  TORCH_CHECK(sparse_feat.dim() == 3 && idx.dim() == 3 && dist2.dim() == 3 && idx.size(2) == 3 && dist2.size(2) == 3,
+              "fused_feature_propagation: sparse_feat (B,Ns,Cs), idx/dist2 (B,Nd,3)");
+  TORCH_CHECK(idx.scalar_type() == at::kLong, "idx must be int64");
+  const auto B = sparse_feat.size(0), Ns = sparse_feat.size(1), Cs = sparse_feat.size(2), Nd = idx.size(1);
+  TORCH_CHECK(idx.size(0) == B && dist2.size(0) == B && dist2.size(1) == Nd, "fused_feature_propagation: shape mismatch");
+  int64_t Cd = 0;
+  const float *sp = nullptr;
+  if (skip.has_value() && skip->defined()) {
+    CHECK_INPUT((*skip)); CHECK_F32((*skip));
+    TORCH_CHECK(skip->dim() == 3 && skip->size(0) == B && skip->size(1) == Nd, "skip must be (B, Nd, Cd)");
+    Cd = skip->size(2);
+    sp = skip->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(sparse_feat.device());
+  Chain ch(wts, biases, relu, out_channels, sparse_feat.device());
+  auto out = at::empty({B, Nd, out_channels}, sparse_feat.options());
+  check_rc(mvp_fused_feature_propagation(sparse_feat.data_ptr<float>(), Cs, idx.data_ptr<int64_t>(), dist2.data_ptr<float>(), sp,
+                                         Cd, B, Ns, Nd, (float)eps, &ch.c, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
 int64_t index_errors_fetch_and_clear() {
   uint64_t n = 0;
   check_rc(mvp_index_errors_fetch_and_clear(cur_stream(), &n));
@@ -264,4 +367,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   auto ds = m.def_submodule("unproject_cuda");
   ds.def("unproject", &unproject, "Depth unprojection (CUDA)");
   ds.def("knn_pixels", &knn_pixels, "2D->3D k-NN over valid pixels (CUDA)");
+  auto fz = m.def_submodule("fused_cuda");
+  fz.def("set_abstraction", &fused_set_abstraction, "gather + MLP + max (CUDA)");
+  fz.def("feature_aggregation", &fused_feature_aggregation, "pixel gather + relation + MLP + sum/max (CUDA)");
+  fz.def("feature_propagation", &fused_feature_propagation, "3-NN interpolate + concat + MLP (CUDA)");
 }

@@ -1,0 +1,285 @@
+"""Fused inference path ("fast path") for the MVPNet hot path on B200.
+
+What the reference runs as ~150 small kernels per chunk (pn2ssg.py:87-118, modules.py, mvpnet_3d.py:88-118)
+— gather, subtract, concat, 3 x (conv, BN, ReLU), max, each round-tripping a (B, C, M, K) tensor
+through HBM — runs here as:
+
+   geometry (depends on xyz only; own stream, overlaps the 2D network)
+       4 x [fps -> centroid gather -> ball_query]   +   4 x knn_distance(3-NN)
+   features
+       feature_aggregation  (pixel gather + relation + MLP + sum)            1 kernel
+       4 x set_abstraction   (neighbour gather + centre + MLP + max)         1 kernel each
+       4 x feature_propagation (weights + interpolate + concat + MLP)        1 kernel each
+       (the segmentation head rides on the last feature_propagation chain)
+
+Tensors between fused kernels are point-major ([B, N, C]); the public (B, C, N) layout of the
+reference is restored at the two ends.  BatchNorm is folded into the weights (eval mode only);
+training uses the op-by-op modules.  Everything here launches kernels of libmvpnet_b200.so — there
+is no eager/CPU fallback inside the fused path; unsupported module configurations fall back to the
+op-by-op CUDA composition in modules.py (still this package's kernels).
+"""
+import contextlib
+
+import torch
+from torch import nn
+
+from . import load_ext
+
+
+# ------------------------------------------------------------------------------------------------
+# optional per-stage timing (bench.py): CUDA events on the stream the stage is launched on
+# ------------------------------------------------------------------------------------------------
+class StageTimer:
+    """with engine.profile() as t: ...forward...; t.summary() -> {stage: [ms, ...]}"""
+
+    def __init__(self):
+        self.records = []
+
+    @contextlib.contextmanager
+    def stage(self, name):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        e.record()
+        self.records.append((name, s, e))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            out.setdefault(name, []).append(s.elapsed_time(e))
+        return out
+
+
+_TIMER = None
+
+
+@contextlib.contextmanager
+def profile():
+    global _TIMER
+    _TIMER = StageTimer()
+    try:
+        yield _TIMER
+    finally:
+        _TIMER = None
+
+
+def _stage(name):
+    return _TIMER.stage(name) if _TIMER is not None else contextlib.nullcontext()
+
+
+# ------------------------------------------------------------------------------------------------
+# weight preparation
+# ------------------------------------------------------------------------------------------------
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _fold(conv, bn):
+    """1x1 conv (+ eval BatchNorm) -> (W [cout, cin], b [cout]) in float64 for a clean fold."""
+    w = conv.weight.detach().double().reshape(conv.out_channels, conv.in_channels)
+    b = conv.bias.detach().double() if conv.bias is not None else torch.zeros(conv.out_channels, dtype=torch.float64, device=w.device)
+    if bn is not None:
+        s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * s[:, None]
+        b = (b - bn.running_mean.detach().double()) * s + bn.bias.detach().double()
+    return w, b
+
+
+class Chain:
+    """A SharedMLP (+ optional extra 1x1 layers) packed for the fused kernels: k-major, zero padded."""
+
+    def __init__(self, layers, cin_true, device):
+        # layers: list of (conv, bn_or_None, relu: bool)
+        self.wts, self.biases, self.relu = [], [], []
+        cin_pad = _round_up(cin_true, 4)
+        for conv, bn, relu in layers:
+            w, b = _fold(conv, bn)
+            cout, cin = w.shape
+            cout_pad = _round_up(cout, 8)
+            wt = torch.zeros(cin_pad, cout_pad, dtype=torch.float64, device=w.device)
+            wt[:cin, :cout] = w.t()
+            bias = torch.zeros(cout_pad, dtype=torch.float64, device=w.device)
+            bias[:cout] = b
+            self.wts.append(wt.float().contiguous().to(device))
+            self.biases.append(bias.float().contiguous().to(device))
+            self.relu.append(1 if relu else 0)
+            cin_pad = cout_pad
+        self.out_channels = layers[-1][0].out_channels
+
+    def args(self):
+        return self.wts, self.biases, self.relu, self.out_channels
+
+
+def _mlp_layers(shared_mlp):
+    return [(m.conv, m.bn, m.relu is not None) for m in shared_mlp]
+
+
+_CACHE = {}
+
+
+def _cached(module, key, build):
+    sig = (key, tuple(int(t._version) for t in module.state_dict().values()),
+           next(module.parameters()).device, module.training)
+    hit = _CACHE.get(id(module))
+    if hit is None or hit[0] != sig:
+        hit = (sig, build())
+        _CACHE[id(module)] = hit
+    return hit[1]
+
+
+def _require_eval_fp32(module, *tensors):
+    if module.training:
+        raise RuntimeError('mvpnet_b200 fused path is inference-only (BatchNorm folded): call .eval() or use forward()')
+    for t in tensors:
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+            raise RuntimeError('mvpnet_b200 fused path needs float32 CUDA tensors')
+
+
+# ------------------------------------------------------------------------------------------------
+# FeatureAggregation
+# ------------------------------------------------------------------------------------------------
+def feature_aggregation(fa, feat2d, image_xyz, knn_indices, points, point_major_out=False):
+    """fa: FeatureAggregation module (eval).  feat2d (b, nv, c, h, w) — the 2D network output viewed per
+    chunk, any memory format; image_xyz (b, nv, h, w, 3); knn_indices (b, np, k); points (b, 3, np).
+    Returns (b, c_out, np) like FeatureAggregation.forward (or (b, np, c_out) when point_major_out).
+    Replaces mvpnet_3d.py:100-109 (both group_points) + :37-61."""
+    ext = load_ext()
+    _require_eval_fp32(fa, feat2d, image_xyz, points)
+    if fa.mlp is None or not fa.use_relation or knn_indices.size(2) > 4:
+        raise RuntimeError('fused feature_aggregation supports use_relation=True, an MLP and k <= 4')
+    b, nv, c, h, w = feat2d.shape
+    chain = _cached(fa, 'fa', lambda: Chain(_mlp_layers(fa.mlp), c + 4, feat2d.device))
+    pix = image_xyz.reshape(b, nv * h * w, 3).contiguous()
+    pts = points.transpose(1, 2).contiguous()
+    with _stage('feature_aggregation'):
+        out = ext.fused_cuda.feature_aggregation(feat2d, pix, pts, knn_indices.contiguous(),
+                                                 fa.reduction_name == 'sum', *chain.args())
+    return out if point_major_out else out.transpose(1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# PN2SSG
+# ------------------------------------------------------------------------------------------------
+def _pn2_supported(net):
+    for sa in net.sa_modules:
+        if sa.num_centroids <= 0 or sa.max_neighbors != 32 or sa.grouper is None:
+            return False
+        if not (sa.use_xyz or sa.in_channels == 3):
+            return False
+    for fp in net.fp_modules:
+        if fp.interpolator is None:
+            return False
+    return True
+
+
+def pn2_geometry(net, xyz_pm):
+    """Everything in PN2SSG.forward that depends on coordinates only (pn2ssg.py:96-110 via
+    modules.py:100-101, 21, 135): per SA level FPS -> centroids -> ball_query; per FP level the 3-NN."""
+    ext = load_ext()
+    levels = [xyz_pm]
+    nbrs = []
+    cur = xyz_pm
+    for i, sa in enumerate(net.sa_modules):
+        with _stage('fps%d' % (i + 1)):
+            idx = ext.fps_cuda.farthest_point_sample(cur, sa.num_centroids)
+        new = torch.gather(cur, 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        with _stage('ball_query%d' % (i + 1)):
+            nbrs.append(ext.ball_query_cuda.ball_query(new, cur, sa.radius, sa.max_neighbors))
+        levels.append(new)
+        cur = new
+    knn = []
+    for i in range(len(net.fp_modules)):
+        with _stage('knn_distance%d' % (i + 1)):
+            knn.append(ext.knn_distance_cuda.knn_distance(levels[-2 - i], levels[-1 - i], 3))
+    return {'xyz': levels, 'nbr': nbrs, 'knn': knn}
+
+
+def _pn2_chains(net, device):
+    sa = []
+    for m in net.sa_modules:
+        sa.append(Chain(_mlp_layers(m.mlp), m.in_channels, device))
+    fp = []
+    for i, m in enumerate(net.fp_modules):
+        layers = _mlp_layers(m.mlp)
+        if i == len(net.fp_modules) - 1:           # segmentation head rides on the last chain
+            layers = layers + _mlp_layers(net.mlp_seg) + [(net.seg_logit, None, False)]
+        fp.append(Chain(layers, m.in_channels, device))
+    return sa, fp
+
+
+def pn2_features(net, geo, feature_pm):
+    """The feature side of PN2SSG.forward on precomputed geometry.  feature_pm (B, N, C) or None.
+    Returns seg_logit (B, num_classes, N)."""
+    ext = load_ext()
+    sa_chains, fp_chains = _cached(net, 'pn2', lambda: _pn2_chains(net, geo['xyz'][0].device))
+    if len(fp_chains[-1].wts) > 6:
+        raise RuntimeError('fused PN2SSG: last FP chain + head exceeds 6 layers')
+    feats = [None]
+    f = feature_pm
+    for i, sa in enumerate(net.sa_modules):
+        src = f if (f is not None) else None
+        with _stage('set_abstraction%d' % (i + 1)):
+            f = ext.fused_cuda.set_abstraction(src, geo['xyz'][i], geo['xyz'][i + 1], geo['nbr'][i], *sa_chains[i].args())
+        feats.append(f)
+    x = feats[-1]
+    for i, fp in enumerate(net.fp_modules):
+        idx, d2 = geo['knn'][i]
+        with _stage('feature_propagation%d' % (i + 1)):
+            x = ext.fused_cuda.feature_propagation(x, idx, d2, feats[-2 - i], fp.interpolator._eps, *fp_chains[i].args())
+    return x.transpose(1, 2).contiguous()
+
+
+def pn2ssg_forward(net, data_batch):
+    """Fused PN2SSG.forward (eval).  data_batch: points (B,3,N), optional feature (B,C,N) or
+    feature_pm (B,N,C)."""
+    points = data_batch['points']
+    feature = data_batch.get('feature', None)
+    feature_pm = data_batch.get('feature_pm', None)
+    _require_eval_fp32(net, points, feature, feature_pm)
+    if not _pn2_supported(net):
+        return net.forward(data_batch)
+    xyz_pm = points.transpose(1, 2).contiguous()
+    if feature_pm is None and feature is not None:
+        feature_pm = feature.transpose(1, 2).contiguous()
+    geo = data_batch.get('geometry', None) or pn2_geometry(net, xyz_pm)
+    return {'seg_logit': pn2_features(net, geo, feature_pm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# MVPNet3D
+# ------------------------------------------------------------------------------------------------
+class _Streams:
+    geo = None
+
+
+def mvpnet3d_forward(model, data_batch, overlap=True):
+    """Fused MVPNet3D.forward (eval): the coordinate-only work of the 3D network runs on a side stream
+    while the 2D network runs; features flow 2D net -> feature_aggregation -> PN2SSG fused chain."""
+    images = data_batch['images']
+    points = data_batch['points']
+    _require_eval_fp32(model, images, points)
+    net3d = model.net_3d
+    if not _pn2_supported(net3d) or model.feat_aggreg.mlp is None or not model.feat_aggreg.use_relation \
+            or data_batch['knn_indices'].size(2) > 4:
+        return model.forward(data_batch)
+    b, nv, _, h, w = images.shape
+    main = torch.cuda.current_stream()
+    xyz_pm = points.transpose(1, 2).contiguous()
+    if overlap:
+        if _Streams.geo is None:
+            _Streams.geo = torch.cuda.Stream()
+        side = _Streams.geo
+        side.wait_stream(main)                     # orders reuse of last call's buffers, keeps overlap
+        with torch.cuda.stream(side):
+            geo = pn2_geometry(net3d, xyz_pm)
+    else:
+        geo = pn2_geometry(net3d, xyz_pm)
+    with _stage('net_2d'):
+        feat2d = model.net_2d.features(images.reshape(b * nv, *images.shape[2:]))
+    feat2d = feat2d.view(b, nv, *feat2d.shape[1:])
+    fa_pm = feature_aggregation(model.feat_aggreg, feat2d, data_batch['image_xyz'], data_batch['knn_indices'],
+                                points, point_major_out=True)
+    if overlap:
+        main.wait_stream(side)
+    return {'seg_logit': pn2_features(net3d, geo, fa_pm)}

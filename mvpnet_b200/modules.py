@@ -265,6 +265,11 @@ class PN2SSG(nn.Module):
         x = self.mlp_seg(x)
         return {'seg_logit': self.seg_logit(x)}
 
+    def fast_forward(self, data_batch):
+        """Inference through the fused sm_100a kernels (mvpnet_b200/engine.py); same result contract."""
+        from . import engine
+        return engine.pn2ssg_forward(self, data_batch)
+
 
 # ------------------------------------------------------------------------------------------- mvpnet
 class FeatureAggregation(nn.Module):
@@ -329,3 +334,8 @@ class MVPNet3D(nn.Module):
         points = data_batch['points']
         feature_2d3d = self.feat_aggreg(image_xyz, points, feature_2d)
         return self.net_3d({'points': points, 'feature': feature_2d3d})
+
+    def fast_forward(self, data_batch, overlap=True):
+        """Inference through the fused sm_100a kernels (mvpnet_b200/engine.py); same result contract."""
+        from . import engine
+        return engine.mvpnet3d_forward(self, data_batch, overlap=overlap)
