@@ -114,9 +114,12 @@ int mvp_unproject(const float *depth, const float *cam_inv, const float *pose,
  * flat pixel ids, mvpnet/data/scannet_2d3d.py:298-313.  query [B,nq,3] f64 (chunk points),
  * pix_xyz [B,P,3] f64, mask [B,P] u8; index out [B,nq,k] int64 flat pixel ids ascending by
  * distance, ties -> lowest id; dist2 [B,nq,k] f64 or NULL.  1 <= k <= 8.  A cloud with fewer than
- * k valid pixels yields -1 in the missing slots (sklearn raises there). */
+ * k valid pixels yields -1 in the missing slots (sklearn raises there).
+ * workspace: mvp_knn_pixels_workspace_bytes() bytes -> exact uniform-grid search (device-built);
+ * NULL -> exhaustive search.  Both return identical results. */
+int64_t mvp_knn_pixels_workspace_bytes(int64_t B, int64_t nq, int64_t P, int64_t k);
 int mvp_knn_pixels(const double *query, const double *pix_xyz, const uint8_t *mask, int64_t B,
-                   int64_t nq, int64_t P, int64_t k, int64_t *index, double *dist2,
+                   int64_t nq, int64_t P, int64_t k, int64_t *index, double *dist2, void *workspace,
                    mvp_stream_t stream);
 
 

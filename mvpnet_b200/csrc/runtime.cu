@@ -18,7 +18,7 @@ void set_error(const char *fmt, ...) {
 
 extern "C" const char *mvp_last_error(void) { return mvp::t_error; }
 
-extern "C" int mvp_abi_version(void) { return 1; }
+extern "C" int mvp_abi_version(void) { return 2; }
 
 extern "C" int mvp_index_errors_fetch_and_clear(mvp_stream_t stream_, uint64_t *count) {
   using namespace mvp;

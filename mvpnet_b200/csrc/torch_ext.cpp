@@ -216,7 +216,7 @@ std::vector<at::Tensor> unproject(const at::Tensor depth, const at::Tensor cam_i
   return {xyz32, mask, want_xyz64 ? xyz64 : at::Tensor()};
 }
 
-std::vector<at::Tensor> knn_pixels(const at::Tensor query, const at::Tensor pix_xyz, const at::Tensor mask, int64_t k) {
+std::vector<at::Tensor> knn_pixels(const at::Tensor query, const at::Tensor pix_xyz, const at::Tensor mask, int64_t k, bool exhaustive) {
   CHECK_INPUT(query);
   CHECK_INPUT(pix_xyz);
   CHECK_INPUT(mask);
@@ -229,9 +229,18 @@ std::vector<at::Tensor> knn_pixels(const at::Tensor query, const at::Tensor pix_
   c10::cuda::CUDAGuard guard(query.device());
   auto index = at::empty({query.size(0), query.size(1), k}, query.options().dtype(at::kLong));
   auto dist2 = at::empty({query.size(0), query.size(1), k}, query.options());
+  at::Tensor work;
+  void *wp = nullptr;
+  if (!exhaustive) {
+    const int64_t ws = mvp_knn_pixels_workspace_bytes(query.size(0), query.size(1), pix_xyz.size(1), k);
+    if (ws > 0) {
+      work = at::empty({ws}, query.options().dtype(at::kByte));
+      wp = work.data_ptr();
+    }
+  }
   check_rc(mvp_knn_pixels(query.data_ptr<double>(), pix_xyz.data_ptr<double>(), (const uint8_t *)mask.data_ptr(),
                           query.size(0), query.size(1), pix_xyz.size(1), k, index.data_ptr<int64_t>(),
-                          dist2.data_ptr<double>(), cur_stream()));
+                          dist2.data_ptr<double>(), wp, cur_stream()));
   return {index, dist2};
 }
 
@@ -366,7 +375,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   ip.def("interpolate_backward", &interpolate_backward, "Interpolate feature backward (CUDA)");
   auto ds = m.def_submodule("unproject_cuda");
   ds.def("unproject", &unproject, "Depth unprojection (CUDA)");
-  ds.def("knn_pixels", &knn_pixels, "2D->3D k-NN over valid pixels (CUDA)");
+  ds.def("knn_pixels", &knn_pixels, "2D->3D k-NN over valid pixels (CUDA)", py::arg("query"), py::arg("pix_xyz"),
+         py::arg("mask"), py::arg("k"), py::arg("exhaustive") = false);
   auto fz = m.def_submodule("fused_cuda");
   fz.def("set_abstraction", &fused_set_abstraction, "gather + MLP + max (CUDA)");
   fz.def("feature_aggregation", &fused_feature_aggregation, "pixel gather + relation + MLP + sum/max (CUDA)");

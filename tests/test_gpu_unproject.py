@@ -62,9 +62,37 @@ def test_knn_pixels(nq, nv, k):
         ii, dd = oracle.knn_pixels(q, flat, m, k)
         qs.append(q); idxs.append(ii); d2s.append(dd); pix.append(flat); msk.append(m.reshape(-1))
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    gi, gd = ext.unproject_cuda.knn_pixels(t(np.stack(qs)), t(np.stack(pix)), t(np.stack(msk).astype(np.uint8)), k)
-    assert np.array_equal(gi.cpu().numpy(), np.stack(idxs))
-    assert np.array_equal(gd.cpu().numpy(), np.stack(d2s))
+    for exhaustive in (False, True):       # uniform-grid search and exhaustive search: identical results
+        gi, gd = ext.unproject_cuda.knn_pixels(t(np.stack(qs)), t(np.stack(pix)), t(np.stack(msk).astype(np.uint8)), k, exhaustive)
+        assert np.array_equal(gi.cpu().numpy(), np.stack(idxs))
+        assert np.array_equal(gd.cpu().numpy(), np.stack(d2s))
+
+
+def test_knn_pixels_grid_edge_cases():
+    """Far / outside-the-box queries, coplanar pixels, exact ties, a single occupied cell."""
+    import mvpnet_b200
+    ext = mvpnet_b200.load_ext()
+    rng = np.random.RandomState(5)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    cases = []
+    # (a) pixels on a plane (zero z extent), lattice => many exact distance ties; queries near and very far
+    gx, gy = np.meshgrid(np.arange(60) * 0.05, np.arange(40) * 0.05)
+    plane = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], 1)
+    q = np.concatenate([plane[rng.choice(len(plane), 200)] + [0.025, 0.025, 0.0], rng.uniform(-30, 30, (56, 3))])
+    cases.append((plane, np.ones(len(plane), np.uint8), q))
+    # (b) all valid pixels identical (one cell), plus masked-out decoys closer to the queries
+    same = np.tile([[1.0, 2.0, 3.0]], (500, 1))
+    decoy = rng.uniform(-1, 1, (500, 3))
+    cases.append((np.concatenate([decoy, same]), np.concatenate([np.zeros(500, np.uint8), np.ones(500, np.uint8)]), rng.uniform(-1, 1, (64, 3))))
+    # (c) two distant clusters: queries between them must walk many empty shells
+    cl = np.concatenate([rng.randn(3000, 3) * 0.05, rng.randn(3000, 3) * 0.05 + [8.0, 0.0, 0.0]])
+    cases.append((cl, np.ones(6000, np.uint8), np.stack([np.linspace(-1, 9, 128), np.zeros(128), np.zeros(128)], 1)))
+    for pix, m, q in cases:
+        for k in (1, 3, 5):
+            want_i, want_d = oracle.knn_pixels(q, pix, m, k)
+            gi, gd = ext.unproject_cuda.knn_pixels(t(q)[None], t(pix)[None], t(m)[None], k, False)
+            assert np.array_equal(gi[0].cpu().numpy(), want_i)
+            assert np.array_equal(gd[0].cpu().numpy(), want_d)
 
 
 def test_knn_pixels_too_few_valid():
@@ -73,5 +101,6 @@ def test_knn_pixels_too_few_valid():
     pix = torch.zeros(1, 10, 3, dtype=torch.float64).cuda()
     mask = torch.zeros(1, 10, dtype=torch.uint8).cuda()
     mask[0, 4] = 1
-    gi, _ = ext.unproject_cuda.knn_pixels(torch.ones(1, 2, 3, dtype=torch.float64).cuda(), pix, mask, 3)
-    assert gi.cpu().numpy().tolist() == [[[4, -1, -1], [4, -1, -1]]]
+    for exhaustive in (False, True):
+        gi, _ = ext.unproject_cuda.knn_pixels(torch.ones(1, 2, 3, dtype=torch.float64).cuda(), pix, mask, 3, exhaustive)
+        assert gi.cpu().numpy().tolist() == [[[4, -1, -1], [4, -1, -1]]]
