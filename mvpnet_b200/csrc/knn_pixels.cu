@@ -270,27 +270,42 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) { bd[j] = Inf<double>::v(); bi[j] = 0x7fffffff; }
 
-  auto scan_range = [&](int c0, int c1) {  // cells c0..c1 of one row (contiguous in the sorted array)
-    const int beg = c0 == 0 ? 0 : ends[c0 - 1];
-    const int end = ends[c1];
+  auto scan = [&](int beg, int end) {  // a contiguous run of the sorted pixel array, lanes in parallel
     for (int p = beg + lane; p < end; p += 32)
       topk_insert<KMAX>(sqdist3_nofma(sx[3 * (size_t)p], sx[3 * (size_t)p + 1], sx[3 * (size_t)p + 2], qx, qy, qz), sid[p], bd, bi);
   };
 
   double kth = Inf<double>::v();   // k-th best squared distance over the whole warp so far
   for (int r = 0; r <= rmax; ++r) {
-    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.gz - 1);
-    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.gy - 1);
+    // Shell r = the (y, z) positions of a (2r+1)^2 square; a position on the square's rim contributes its
+    // whole x extent [cx-r, cx+r] (one contiguous run), an interior position only its two end cells.
+    // Lanes fetch the run boundaries of 32 positions at once (the dependent loads are the latency of this
+    // kernel), then the warp streams the non-empty runs cooperatively.
+    const int side = 2 * r + 1, npos = side * side;
     const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
-    for (int z = z0; z <= z1; ++z) {
-      for (int y = y0; y <= y1; ++y) {
-        const int row = (z * g.gy + y) * g.gx;
-        if (abs(z - cz) == r || abs(y - cy) == r) {
-          scan_range(row + x0, row + x1);               // a face row of the shell: the whole x extent
-        } else {                                        // interior row: only the two end cells
-          if (cx - r >= 0) scan_range(row + cx - r, row + cx - r);
-          if (cx + r < g.gx && r > 0) scan_range(row + cx + r, row + cx + r);
+    for (int base = 0; base < npos; base += 32) {
+      const int t = base + lane;
+      int beg0 = 0, end0 = 0, beg1 = 0, end1 = 0;
+      if (t < npos) {
+        const int dz = t / side - r, dy = t - (t / side) * side - r;
+        const int z = cz + dz, y = cy + dy;
+        if (z >= 0 && z < g.gz && y >= 0 && y < g.gy) {
+          const int row = (z * g.gy + y) * g.gx;
+          if (abs(dz) == r || abs(dy) == r) {
+            beg0 = row + x0 == 0 ? 0 : ends[row + x0 - 1];
+            end0 = ends[row + x1];
+          } else {
+            if (cx - r >= 0) { const int c = row + cx - r; beg0 = c == 0 ? 0 : ends[c - 1]; end0 = ends[c]; }
+            if (cx + r < g.gx) { const int c = row + cx + r; beg1 = ends[c - 1]; end1 = ends[c]; }
+          }
         }
+      }
+      unsigned active = __ballot_sync(0xffffffffu, end0 > beg0 || end1 > beg1);
+      while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        scan(__shfl_sync(0xffffffffu, beg0, src), __shfl_sync(0xffffffffu, end0, src));
+        scan(__shfl_sync(0xffffffffu, beg1, src), __shfl_sync(0xffffffffu, end1, src));
       }
     }
     // k-th smallest over the 32 sorted lists (non-destructive merge)
