@@ -16,8 +16,9 @@
  *   - return value: 0 on success; MVP_ERR_* (<0) for argument errors (the reference raises
  *     RuntimeError via TORCH_CHECK / CHECK_EQ there); >0 is a cudaError_t from the launch
  *   - mvp_last_error() returns a thread-local message for the last non-zero return
- *   - arithmetic contract: squared distances are fma(dz,dz, fma(dy,dy, dx*dx)) with d = key - query
- *     in the input dtype (what nvcc -O2 emits for the reference loops), comparisons strict
+ *   - arithmetic contract: squared distances with d = key - query in the input dtype are
+ *     float fma(dz,dz, fma(dy,dy, dx*dx)), double fma(dz,dz, fma(dx,dx, dy*dy)) — what nvcc -O2 emits
+ *     for the reference loops on sm_100a (checked against the built reference kernels); comparisons strict
  */
 #ifndef MVPNET_B200_H_
 #define MVPNET_B200_H_

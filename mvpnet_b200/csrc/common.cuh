@@ -43,16 +43,29 @@ inline int sm_count() {
   } while (0)
 
 // ---- arithmetic contract -----------------------------------------------------------------------
-// d^2 = fma(dz,dz, fma(dy,dy, dx*dx)), d = key - query: the exact sequence nvcc -O2 emits for the
-// reference's `dist += diff * diff` loops (ball_query_kernel.cu:111-116 et al.).  Spelled with
-// intrinsics so no compiler flag can change it.
+// Squared distance, d = key - query, in the exact sequence nvcc -O2 emits for the reference's
+// `dist = 0; dist += diff * diff` loops (ball_query_kernel.cu:111-116 et al.), read off the SASS of the
+// reference sources built for sm_100a (oracle/build_ref.py) and checked bit-for-bit against those
+// kernels in tests/test_gpu_vs_reference_kernels.py:
+//   float :  fma(dz,dz, fma(dy,dy, dx*dx))        double:  fma(dz,dz, fma(dx,dx, dy*dy))
+// Spelled with intrinsics so no compiler flag can change it.
 __device__ __forceinline__ float sqdist3(float kx, float ky, float kz, float qx, float qy, float qz) {
   const float dx = __fsub_rn(kx, qx), dy = __fsub_rn(ky, qy), dz = __fsub_rn(kz, qz);
   return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 __device__ __forceinline__ double sqdist3(double kx, double ky, double kz, double qx, double qy, double qz) {
   const double dx = __dsub_rn(kx, qx), dy = __dsub_rn(ky, qy), dz = __dsub_rn(kz, qz);
-  return __fma_rn(dz, dz, __fma_rn(dy, dy, __dmul_rn(dx, dx)));
+  return __fma_rn(dz, dz, __fma_rn(dx, dx, __dmul_rn(dy, dy)));
+}
+
+// 2-D variant (FPS accepts (B, N, 2) points): float fma(dy,dy, dx*dx), double fma(dx,dx, dy*dy)
+__device__ __forceinline__ float sqdist2(float kx, float ky, float qx, float qy) {
+  const float dx = __fsub_rn(kx, qx), dy = __fsub_rn(ky, qy);
+  return __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+}
+__device__ __forceinline__ double sqdist2(double kx, double ky, double qx, double qy) {
+  const double dx = __dsub_rn(kx, qx), dy = __dsub_rn(ky, qy);
+  return __fma_rn(dx, dx, __dmul_rn(dy, dy));
 }
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }

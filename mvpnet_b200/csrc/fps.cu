@@ -126,8 +126,7 @@ fps_generic_kernel(const T *__restrict__ points, int64_t *__restrict__ index, T 
       if (D == 3) {
         dist = sqdist3(a[0], a[1], a[2], c[0], c[1], c[2]);
       } else {
-        const T dx = a[0] - c[0], dy = a[1] - c[1];
-        dist = fma(dy, dy, dx * dx);
+        dist = sqdist2(a[0], a[1], c[0], c[1]);
       }
       const T last = tmp[j];
       if (dist < last) tmp[j] = dist; else dist = last;

@@ -2,13 +2,20 @@
  * TEST INFRASTRUCTURE ONLY — body of the CPU oracle, included once per scalar type by
  * mvp_oracle.c (T = float / double).  See mvp_oracle.c for the contract.
  *
- * Required macros: T (scalar type), SFX (symbol suffix), FMA(a,b,c) (fused multiply-add in T).
+ * Required macros: T (scalar type), SFX (symbol suffix), FMA(a,b,c) (fused multiply-add in T),
+ * SQ3(dx,dy,dz) / SQ2(dx,dy) (squared norm in the reference's contraction order).
  *
  * Arithmetic note (reference: mvpnet/ops/setup.py:22 builds with plain `nvcc -O2`, i.e. the
- * default -fmad=true): every `dist += diff * diff` loop in the reference kernels is contracted by
- * nvcc into  d = dx*dx ; d = fma(dy,dy,d) ; d = fma(dz,dz,d)  (first term is fma(dx,dx,0) ==
- * dx*dx).  The oracle spells that chain out so that near-threshold / near-tie cases resolve the
- * same way as on the GPU.
+ * default -fmad=true): every `dist = 0; dist += diff * diff` loop in the reference kernels is
+ * contracted by nvcc.  What it contracts TO was read off the SASS of the reference sources built
+ * unmodified for sm_100a with nvcc 12.9 (oracle/build_ref.py, `cuobjdump -sass oracle/_ref/*.so`)
+ * and is confirmed bit-for-bit by tests/test_gpu_vs_reference_kernels.py:
+ *     float :  FFMA(dx,dx,0) ; FFMA(dy,dy,.) ; FFMA(dz,dz,.)   ==  fma(dz,dz, fma(dy,dy, dx*dx))
+ *     double:  DMUL(dy,dy)   ; DFMA(dx,dx,.) ; DFMA(dz,dz,.)   ==  fma(dz,dz, fma(dx,dx, dy*dy))
+ * (in double the `0.0 +` is folded away and, of the two products then being added, the FIRST one
+ * is fused while the second is rounded).  2-D points (FPS only): float fma(dy,dy, dx*dx), double
+ * fma(dx,dx, dy*dy).  The oracle spells these chains out so that near-threshold / near-tie cases
+ * resolve exactly as on the GPU.
  */
 
 #define CAT_(a, b) a##b
@@ -18,10 +25,7 @@
 /* squared distance with the reference's contraction order; diff = key - query */
 static inline T FN(sqdist3)(const T *a, const T *q) {
   T dx = a[0] - q[0], dy = a[1] - q[1], dz = a[2] - q[2];
-  T d = dx * dx;
-  d = FMA(dy, dy, d);
-  d = FMA(dz, dz, d);
-  return d;
+  return SQ3(dx, dy, dz);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -55,11 +59,9 @@ int FN(mvpo_fps)(const T *points, int64_t B, int64_t N, int64_t D, int64_t M, in
         T max_dist = (T)0.0;
         int max_idx = cur;
         for (int64_t j = t; j < N; j += BS) {
-          T dist = (T)0.0;
-          for (int d = 0; d < D; ++d) {
-            T diff = pts[j * D + d] - c[d];
-            dist = FMA(diff, diff, dist);
-          }
+          T dist;
+          if (D == 3) dist = SQ3(pts[j * 3] - c[0], pts[j * 3 + 1] - c[1], pts[j * 3 + 2] - c[2]);
+          else dist = SQ2(pts[j * 2] - c[0], pts[j * 2 + 1] - c[1]);
           T last = temp[j];
           if (last > dist || last < (T)0.0) temp[j] = dist; else dist = last;
           if (dist > max_dist) { max_dist = dist; max_idx = (int)j; }
