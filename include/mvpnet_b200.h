@@ -174,6 +174,38 @@ int mvp_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const in
                                   const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
                                   const mvp_mlp_chain_t *chain, float *out, mvp_stream_t stream);
 
+/* ==== tensor-core variants of the fused kernels (tcgen05 / TMEM, bf16 hi/lo split x 3 products) ======
+ * Same contracts as the three mvp_fused_* calls above.  mvp_tc_chain_t: layer l has K = k[l] input
+ * channels (multiple of 16; k[0] >= width of the built row, zero padded; k[l+1] == n[l]) and N = n[l]
+ * output channels (multiple of 16, <= 512).  Weights (BatchNorm folded) are split on the host into
+ * bf16 w_hi = bf16(w), w_lo = bf16(w - w_hi) and stored in the kernel's operand order: for every
+ * 256-wide block of output channels n0: [k/8][min(256, n - n0)][8] bf16 (K-slab major).  bias fp32 [n].
+ * Feature channel counts must be multiples of 8.  mvp_tc_chain_supported() tells whether a chain's
+ * activation tile fits shared memory / TMEM (mode 0 = set abstraction, 1 = aggregation, 2 = propagation). */
+typedef struct {
+  int32_t num_layers;
+  int32_t k[MVP_MLP_MAX_LAYERS];
+  int32_t n[MVP_MLP_MAX_LAYERS];
+  int32_t relu[MVP_MLP_MAX_LAYERS];
+  const void *w_hi[MVP_MLP_MAX_LAYERS];
+  const void *w_lo[MVP_MLP_MAX_LAYERS];
+  const float *bias[MVP_MLP_MAX_LAYERS];
+  int32_t out_channels;
+} mvp_tc_chain_t;
+
+int mvp_tc_chain_supported(const mvp_tc_chain_t *chain, int mode);
+int mvp_tc_fused_set_abstraction(const float *feat, int64_t C, const float *xyz, const float *new_xyz,
+                                 const int64_t *nbr, int64_t B, int64_t N, int64_t M, int64_t K,
+                                 const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream);
+int mvp_tc_fused_feature_aggregation(const float *feat2d, int64_t s_n, int64_t s_c, int64_t s_h, int64_t s_w,
+                                     int64_t C, int64_t nv, int64_t h, int64_t w, const float *pix_xyz,
+                                     const float *points, const int64_t *knn, int64_t B, int64_t Np, int64_t K,
+                                     int reduce_sum, const mvp_tc_chain_t *chain, float *out,
+                                     mvp_stream_t stream);
+int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const int64_t *idx, const float *dist2,
+                                     const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
+                                     const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,3 +9,4 @@
 #include "unproject.cu"
 #include "knn_pixels.cu"
 #include "fused_mlp.cu"
+#include "tc_mlp.cu"

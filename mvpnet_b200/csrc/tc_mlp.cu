@@ -1,0 +1,532 @@
+// Tensor-core (tcgen05 / TMEM) version of the fused "build rows -> MLP chain -> reduce" kernel, sm_100a.
+//
+// Same contract as fused_mlp.cu (MODE_SA / MODE_FA / MODE_FP, reference lines cited there); this file
+// moves the 1x1-conv chain onto the 5th-generation tensor cores:
+//
+//   * tile = 128 rows (UMMA M = 128, cta_group::1): SA 4 centroids x 32 neighbours, FA 32 points x 3
+//     pixels (+32 idle rows), FP 128 points.  Accumulators live in TMEM (128 lanes x Cout columns fp32).
+//   * precision: every fp32 operand is split into bf16 hi + bf16 lo and each K-step issues THREE
+//     tcgen05.mma.kind::f16 into the same accumulator: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi (fp32 accumulate).
+//     On the reference modules this reproduces the golden logits to 1.6e-5 (single-pass bf16/tf32: 4e-3..8e-3;
+//     the bar is 1e-4) at twice the MMA rate and half the operand bytes of a 3xTF32 scheme.
+//   * operands are K-major, no-swizzle canonical UMMA layout: 8-row x 16-byte core matrices, a K-slab
+//     (8 channels x all rows) is contiguous, so the epilogue of layer l writes layer l+1's A operand with
+//     conflict-free 16-byte stores (one thread = one row = one TMEM lane).
+//   * a layer's MMAs are all issued (one elected thread) before its epilogue runs, so the activation
+//     buffer is rewritten IN PLACE; weights stream through a 2-stage shared-memory ring whose stages are
+//     released by tcgen05.commit -> mbarrier; the host pre-arranges W_hi / W_lo in exactly the ring layout.
+//   * SA epilogue: one warp reads the 32 TMEM lanes of one centroid (tcgen05.ld 32x32b), so the max over
+//     the K = 32 neighbours is a warp shuffle reduction.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mvp {
+namespace tc {
+
+constexpr int ROWS = 128;
+constexpr int THREADS = 256;
+constexpr int MAX_LAYERS = 6;
+constexpr int SLAB = ROWS * 16;  // bytes of one K-slab (8 channels) of the A operand
+
+struct Chain {
+  int num_layers;
+  int k[MAX_LAYERS];      // padded to a multiple of 16
+  int n[MAX_LAYERS];      // padded to a multiple of 16, <= 512; k[l+1] == n[l]
+  int relu[MAX_LAYERS];
+  const __nv_bfloat16 *w_hi[MAX_LAYERS];  // per 256-wide N block: [k/8][nb][8]
+  const __nv_bfloat16 *w_lo[MAX_LAYERS];
+  const float *bias[MAX_LAYERS];          // [n]
+  int out_channels;
+  int kc;                 // K elements per weight chunk (16 or 32)
+  int kmax;               // max k over layers
+  int nbmax;              // max N-block width over layers (<= 256)
+  int tmem_cols;          // power of two >= max n, >= 32
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm100):
+// start address >> 4 [0,14), leading (K-direction) byte offset >> 4 [16,30), stride (M/N-direction) byte
+// offset >> 4 [32,46), version [46,48), layout type [61,64) = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6)=1, A = B = BF16 [7,10),[10,13)=1,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand packing ---------------------------------------------------------------------------
+// 8 consecutive channels of one row -> one 16-byte unit of the hi operand and one of the lo operand
+__device__ __forceinline__ void store8(unsigned char *a_hi, unsigned char *a_lo, int row, int kb, const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  const size_t off = (size_t)kb * SLAB + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16;
+  *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void load8(const float *p, bool ok, float (&v)[8]) {
+  if (ok) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  }
+}
+
+// ---- row builders (one warp per row, lanes over 8-channel groups) -------------------------------
+__device__ __forceinline__ void build_sa(const BuildArgs &a, unsigned char *a_hi, unsigned char *a_lo, int kblocks, long long tile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.feat_channels, cb = C >> 3;
+  for (int r = warp; r < ROWS; r += THREADS / 32) {
+    const long long gid = tile * 4 + (r >> 5);
+    long long j = -1, b = 0;
+    if (gid < a.rows_out) { b = gid / a.n_out; j = a.nbr[gid * 32 + (r & 31)]; }
+    const bool ok = j >= 0 && j < a.n_src;
+    const float *src = a.feat + ((size_t)b * a.n_src + (ok ? j : 0)) * C;
+    for (int kb = lane; kb < kblocks; kb += 32) {
+      float v[8];
+      if (kb < cb) {
+        load8(src + kb * 8, ok, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (kb == cb && ok) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            v[i] = __fsub_rn(__ldg(a.xyz + ((size_t)b * a.n_src + j) * 3 + i), __ldg(a.new_xyz + gid * 3 + i));
+        }
+      }
+      store8(a_hi, a_lo, r, kb, v);
+    }
+  }
+}
+
+__device__ __forceinline__ void build_fa(const BuildArgs &a, unsigned char *a_hi, unsigned char *a_lo, int kblocks, long long tile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.feat_channels, cb = C >> 3;
+  for (int r = warp; r < ROWS; r += THREADS / 32) {
+    const int i = r >> 5, p = r & 31;
+    const long long pid = tile * 32 + p;
+    long long j = -1, b = 0;
+    if (pid < a.rows_out && i < a.k) { b = pid / a.n_out; j = a.nbr[pid * a.k + i]; }
+    const bool ok = j >= 0 && j < a.n_src;
+    const long long jj = ok ? j : 0;
+    const int v_ = (int)(jj / a.hw), pix = (int)(jj - (long long)v_ * a.hw);
+    const int y = pix / a.w, x = pix - y * a.w;
+    const float *src = a.feat + ((size_t)b * a.nv + v_) * a.s_n + (size_t)y * a.s_h + (size_t)x * a.s_w;
+    for (int kb = lane; kb < kblocks; kb += 32) {
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] = 0.f;
+      if (kb < cb) {
+        if (a.s_c == 1) load8(src + kb * 8, ok, v);
+        else if (ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = __ldg(src + (size_t)(kb * 8 + c) * a.s_c);
+        }
+      } else if (kb == cb && ok) {
+        const float *s = a.xyz + ((size_t)b * a.n_src + j) * 3;
+        const float *t = a.new_xyz + pid * 3;
+        v[0] = __fsub_rn(__ldg(s), __ldg(t)); v[1] = __fsub_rn(__ldg(s + 1), __ldg(t + 1)); v[2] = __fsub_rn(__ldg(s + 2), __ldg(t + 2));
+        v[3] = __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));
+      }
+      store8(a_hi, a_lo, r, kb, v);
+    }
+  }
+}
+
+__device__ __forceinline__ void build_fp(const BuildArgs &a, unsigned char *a_hi, unsigned char *a_lo, int kblocks, long long tile) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Cs = a.feat_channels, Cd = a.skip_channels, sb = Cs >> 3, db = Cd >> 3;
+  for (int r = warp; r < ROWS; r += THREADS / 32) {
+    const long long pid = tile * ROWS + r;
+    const bool live = pid < a.rows_out;
+    const long long b = live ? pid / a.n_out : 0;
+    float w[3] = {0.f, 0.f, 0.f};
+    long long j[3] = {0, 0, 0};
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        j[k] = a.nbr[pid * 3 + k];
+        w[k] = __fdiv_rn(1.0f, fmaxf(__ldg(a.dist + pid * 3 + k), a.eps));
+        if (j[k] < 0 || j[k] >= a.n_src) { j[k] = 0; w[k] = 0.f; }
+      }
+      const float norm = __fadd_rn(__fadd_rn(w[0], w[1]), w[2]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) w[k] = __fdiv_rn(w[k], norm);
+    }
+    const float *s0 = a.feat + ((size_t)b * a.n_src + j[0]) * Cs;
+    const float *s1 = a.feat + ((size_t)b * a.n_src + j[1]) * Cs;
+    const float *s2 = a.feat + ((size_t)b * a.n_src + j[2]) * Cs;
+    for (int kb = lane; kb < kblocks; kb += 32) {
+      float v[8];
+      if (kb < sb) {
+        float v0[8], v1[8], v2[8];
+        load8(s0 + kb * 8, live, v0); load8(s1 + kb * 8, live, v1); load8(s2 + kb * 8, live, v2);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __fmaf_rn(v2[c], w[2], __fmaf_rn(v1[c], w[1], __fmul_rn(v0[c], w[0])));
+      } else if (kb < sb + db) {
+        load8(a.skip + (size_t)pid * Cd + (kb - sb) * 8, live, v);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = 0.f;
+      }
+      store8(a_hi, a_lo, r, kb, v);
+    }
+  }
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, long long num_tiles) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t a_bytes = (size_t)(m.kmax >> 3) * SLAB;
+  const size_t stage_half = (size_t)(m.kc >> 3) * m.nbmax * 16;  // one of {hi, lo} of one ring stage
+  unsigned char *a_hi = smem, *a_lo = smem + a_bytes;
+  unsigned char *ring = smem + 2 * a_bytes;                      // [stage][hi|lo]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + 4 * stage_half);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+  const uint32_t bar_w0 = smem_u32(bars), bar_w1 = smem_u32(bars + 1), bar_done = smem_u32(bars + 2);
+
+  if (tid == 0) {
+    mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)m.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  uint32_t ring_it = 0;      // number of ring chunks issued so far (all threads count identically)
+  uint32_t done_phase = 0;
+
+  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (MODE == MODE_SA) build_sa(a, a_hi, a_lo, m.k[0] >> 3, tile);
+    else if (MODE == MODE_FA) build_fa(a, a_hi, a_lo, m.k[0] >> 3, tile);
+    else build_fp(a, a_hi, a_lo, m.k[0] >> 3, tile);
+    fence_proxy_async();
+    __syncthreads();
+
+    for (int l = 0; l < m.num_layers; ++l) {
+      const int K = m.k[l], N = m.n[l];
+      const bool last = l == m.num_layers - 1;
+      // ---- MMAs of the layer: N blocks of <= 256 columns, K chunks of m.kc through the ring
+      for (int n0 = 0; n0 < N; n0 += 256) {
+        const int nb = min(256, N - n0);
+        const uint32_t idesc = make_idesc(ROWS, nb);
+        const unsigned char *gw_hi = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2;
+        const unsigned char *gw_lo = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2;
+        for (int k0 = 0; k0 < K; k0 += m.kc) {
+          const int kc = min(m.kc, K - k0);
+          const uint32_t s = ring_it & 1u, use = ring_it >> 1;
+          if (use > 0) mbar_wait(s ? bar_w1 : bar_w0, (use - 1) & 1u);  // MMAs of the previous use have drained
+          unsigned char *st_hi = ring + (size_t)s * 2 * stage_half, *st_lo = st_hi + stage_half;
+          const size_t chunk_bytes = (size_t)(kc >> 3) * nb * 16;
+          const size_t goff = (size_t)(k0 >> 3) * nb * 16;
+          for (size_t o = (size_t)tid * 16; o < chunk_bytes; o += THREADS * 16) {
+            *reinterpret_cast<uint4 *>(st_hi + o) = __ldg(reinterpret_cast<const uint4 *>(gw_hi + goff + o));
+            *reinterpret_cast<uint4 *>(st_lo + o) = __ldg(reinterpret_cast<const uint4 *>(gw_lo + goff + o));
+          }
+          fence_proxy_async();
+          __syncthreads();
+          if (tid == 0) {
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)n0;
+            for (int j = 0; j < kc; j += 16) {
+              const uint32_t ks = (uint32_t)((k0 + j) >> 3);  // first of the two K-slabs of this step
+              const uint64_t ah = make_desc(smem_u32(a_hi + (size_t)ks * SLAB), SLAB, 128);
+              const uint64_t al = make_desc(smem_u32(a_lo + (size_t)ks * SLAB), SLAB, 128);
+              const uint64_t wh = make_desc(smem_u32(st_hi + (size_t)(j >> 3) * nb * 16), (uint32_t)nb * 16, 128);
+              const uint64_t wl = make_desc(smem_u32(st_lo + (size_t)(j >> 3) * nb * 16), (uint32_t)nb * 16, 128);
+              umma_bf16(d_tmem, ah, wh, idesc, (k0 + j) > 0 ? 1u : 0u);
+              umma_bf16(d_tmem, ah, wl, idesc, 1u);
+              umma_bf16(d_tmem, al, wh, idesc, 1u);
+            }
+            umma_commit(s ? bar_w1 : bar_w0);
+          }
+          ++ring_it;
+        }
+      }
+      if (tid == 0) umma_commit(bar_done);
+      mbar_wait(bar_done, done_phase);
+      done_phase ^= 1u;
+      tc_fence_after();
+
+      // ---- epilogue: thread = row (TMEM lane 32*(warp&3) + lane); warps 0-3 / 4-7 take alternate 16-column chunks
+      const int row = (warp & 3) * 32 + lane;
+      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      float *fbuf = reinterpret_cast<float *>(smem);  // MODE_FA last layer: [ROWS][N] fp32 staging over the (dead) A operand
+      for (int c = (warp >> 2); c * 16 < N; c += 2) {
+        float v[16];
+        tmem_ld16(t_lane + (uint32_t)(c * 16), v);
+        const float4 *bp = reinterpret_cast<const float4 *>(m.bias[l] + c * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bq = __ldg(bp + q);
+          v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+        }
+        if (m.relu[l]) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (!last) {
+          float lo8[8], hi8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { lo8[i] = v[i]; hi8[i] = v[8 + i]; }
+          store8(a_hi, a_lo, row, 2 * c, lo8);
+          store8(a_hi, a_lo, row, 2 * c + 1, hi8);
+        } else if (MODE == MODE_SA) {
+          const long long gid = tile * 4 + (warp & 3);
+          float keep = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+            if (lane == i) keep = x;
+          }
+          const int col = c * 16 + lane;
+          if (lane < 16 && col < m.out_channels && gid < a.rows_out) out[gid * m.out_channels + col] = keep;
+        } else if (MODE == MODE_FP) {
+          const long long pid = tile * ROWS + row;
+          if (pid < a.rows_out) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c * 16 + i < m.out_channels) out[pid * m.out_channels + c * 16 + i] = v[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) fbuf[(size_t)row * N + c * 16 + i] = v[i];
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncthreads();
+      tc_fence_after();
+      if (last && MODE == MODE_FA) {
+        for (int e = tid; e < 32 * m.out_channels; e += THREADS) {
+          const int p = e / m.out_channels, c = e - p * m.out_channels;
+          const long long pid = tile * 32 + p;
+          if (pid >= a.rows_out) continue;
+          float v = fbuf[(size_t)p * N + c];
+          for (int i = 1; i < a.k; ++i) {
+            const float u = fbuf[(size_t)(i * 32 + p) * N + c];
+            v = a.reduce == REDUCE_SUM ? __fadd_rn(v, u) : fmaxf(v, u);
+          }
+          out[pid * m.out_channels + c] = v;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)m.tmem_cols);
+}
+
+static size_t smem_bytes(const Chain &m) {
+  return (size_t)(m.kmax >> 3) * SLAB * 2 + (size_t)4 * (m.kc >> 3) * m.nbmax * 16 + 64;
+}
+
+// fills the derived fields; returns false when the chain does not fit this kernel
+static bool finalize(Chain &m, int mode) {
+  m.kmax = 0;
+  m.nbmax = 0;
+  int nmax = 0;
+  for (int l = 0; l < m.num_layers; ++l) {
+    if (m.k[l] > m.kmax) m.kmax = m.k[l];
+    const int nb = m.n[l] < 256 ? m.n[l] : 256;
+    if (nb > m.nbmax) m.nbmax = nb;
+    if (m.n[l] > nmax) nmax = m.n[l];
+  }
+  if (nmax > 512) return false;
+  m.tmem_cols = 32;
+  while (m.tmem_cols < nmax) m.tmem_cols <<= 1;
+  if (mode == MODE_FA && m.n[m.num_layers - 1] > m.kmax) return false;  // fp32 staging [128][N] must fit in the A operand (kmax * 512 B)
+  for (m.kc = 32; m.kc >= 16; m.kc >>= 1)
+    if (smem_bytes(m) <= 227 * 1024) return true;
+  return false;
+}
+
+template <int MODE>
+static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cudaStream_t stream) {
+  auto kern = tc_fused_mlp_kernel<MODE>;
+  const size_t smem = smem_bytes(m);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("tc_fused_mlp: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+  // persistent: as many CTAs as fit (shared memory and TMEM columns bound the residency)
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm * m.tmem_cols > 512) per_sm = 512 / m.tmem_cols;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  long long grid = (long long)sm_count() * per_sm;
+  if (grid > tiles) grid = tiles;
+  kern<<<(unsigned)grid, THREADS, smem, stream>>>(a, m, out, tiles);
+  return launch_status("tc_fused_mlp");
+}
+
+}  // namespace tc
+}  // namespace mvp
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+static int mvp_tc_to_chain(const mvp_tc_chain_t *c, int k0_min, int mode, mvp::tc::Chain *m) {
+  using namespace mvp;
+  MVP_REQUIRE(c, MVP_ERR_NULL, "tc_fused_mlp: null chain");
+  MVP_REQUIRE(c->num_layers >= 1 && c->num_layers <= tc::MAX_LAYERS, MVP_ERR_INVALID_ARG, "tc_fused_mlp: 1..6 layers");
+  MVP_REQUIRE(c->k[0] >= k0_min, MVP_ERR_INVALID_ARG, "tc_fused_mlp: k[0]=%d < %d input channels", c->k[0], k0_min);
+  m->num_layers = c->num_layers;
+  m->out_channels = c->out_channels;
+  for (int l = 0; l < c->num_layers; ++l) {
+    MVP_REQUIRE(c->k[l] % 16 == 0 && c->n[l] % 16 == 0 && c->k[l] > 0 && c->n[l] > 0, MVP_ERR_INVALID_ARG,
+                "tc_fused_mlp: k and n must be positive multiples of 16");
+    MVP_REQUIRE(l == 0 || c->k[l] == c->n[l - 1], MVP_ERR_INVALID_ARG, "tc_fused_mlp: k[l] must equal n[l-1]");
+    MVP_REQUIRE(c->w_hi[l] && c->w_lo[l] && c->bias[l], MVP_ERR_NULL, "tc_fused_mlp: null weights");
+    MVP_REQUIRE((((uintptr_t)c->w_hi[l] | (uintptr_t)c->w_lo[l] | (uintptr_t)c->bias[l]) & 15) == 0, MVP_ERR_INVALID_ARG,
+                "tc_fused_mlp: weights must be 16-byte aligned");
+    m->k[l] = c->k[l]; m->n[l] = c->n[l]; m->relu[l] = c->relu[l];
+    m->w_hi[l] = (const __nv_bfloat16 *)c->w_hi[l]; m->w_lo[l] = (const __nv_bfloat16 *)c->w_lo[l]; m->bias[l] = c->bias[l];
+  }
+  MVP_REQUIRE(c->out_channels > 0 && c->out_channels <= c->n[c->num_layers - 1], MVP_ERR_INVALID_ARG, "tc_fused_mlp: bad out_channels");
+  MVP_REQUIRE(tc::finalize(*m, mode), MVP_ERR_UNSUPPORTED, "tc_fused_mlp: chain too wide for shared memory / TMEM (kmax=%d)", m->kmax);
+  return 0;
+}
+
+extern "C" int mvp_tc_chain_supported(const mvp_tc_chain_t *c, int mode) {
+  mvp::tc::Chain m;
+  if (!c || c->num_layers < 1 || c->num_layers > mvp::tc::MAX_LAYERS) return 0;
+  m.num_layers = c->num_layers;
+  for (int l = 0; l < c->num_layers; ++l) { m.k[l] = c->k[l]; m.n[l] = c->n[l]; }
+  return mvp::tc::finalize(m, mode) ? 1 : 0;
+}
+
+extern "C" int mvp_tc_fused_set_abstraction(const float *feat, int64_t C, const float *xyz, const float *new_xyz,
+                                            const int64_t *nbr, int64_t B, int64_t N, int64_t M, int64_t K,
+                                            const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(K == 32, MVP_ERR_UNSUPPORTED, "tc_fused_set_abstraction: max_neighbors must be 32");
+  MVP_REQUIRE(C % 8 == 0 && C >= 0, MVP_ERR_UNSUPPORTED, "tc_fused_set_abstraction: feature channels must be a multiple of 8");
+  MVP_REQUIRE(B >= 0 && N > 0 && M >= 0, MVP_ERR_INVALID_ARG, "tc_fused_set_abstraction: bad sizes");
+  tc::Chain m;
+  if (int rc = mvp_tc_to_chain(chain, (int)C + 3, MODE_SA, &m)) return rc;
+  if (B * M == 0) return 0;
+  MVP_REQUIRE(xyz && new_xyz && nbr && out && (feat || C == 0), MVP_ERR_NULL, "tc_fused_set_abstraction: null pointer");
+  MVP_REQUIRE(((uintptr_t)feat & 15) == 0, MVP_ERR_INVALID_ARG, "tc_fused_set_abstraction: feat must be 16-byte aligned");
+  BuildArgs a = {};
+  a.rows_out = B * M; a.feat_channels = (int)C; a.feat = feat; a.xyz = xyz; a.new_xyz = new_xyz; a.nbr = nbr;
+  a.n_src = N; a.n_out = M; a.k = 32;
+  return tc::launch<MODE_SA>(a, m, out, (a.rows_out + 3) / 4, (cudaStream_t)stream);
+}
+
+extern "C" int mvp_tc_fused_feature_aggregation(const float *feat2d, int64_t s_n, int64_t s_c, int64_t s_h, int64_t s_w,
+                                                int64_t C, int64_t nv, int64_t h, int64_t w, const float *pix_xyz,
+                                                const float *points, const int64_t *knn, int64_t B, int64_t Np, int64_t K,
+                                                int reduce_sum, const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(K >= 1 && K <= 4, MVP_ERR_UNSUPPORTED, "tc_fused_feature_aggregation: k must be in [1, 4]");
+  MVP_REQUIRE(C % 8 == 0 && C > 0, MVP_ERR_UNSUPPORTED, "tc_fused_feature_aggregation: feature channels must be a multiple of 8");
+  MVP_REQUIRE(B >= 0 && Np >= 0 && nv > 0 && h > 0 && w > 0, MVP_ERR_INVALID_ARG, "tc_fused_feature_aggregation: bad sizes");
+  tc::Chain m;
+  if (int rc = mvp_tc_to_chain(chain, (int)C + 4, MODE_FA, &m)) return rc;
+  if (B * Np == 0) return 0;
+  MVP_REQUIRE(feat2d && pix_xyz && points && knn && out, MVP_ERR_NULL, "tc_fused_feature_aggregation: null pointer");
+  if (s_c == 1)
+    MVP_REQUIRE((((uintptr_t)feat2d) & 15) == 0 && s_n % 4 == 0 && s_h % 4 == 0 && s_w % 4 == 0, MVP_ERR_UNSUPPORTED,
+                "tc_fused_feature_aggregation: channels-last feature map must be 16-byte aligned per pixel");
+  BuildArgs a = {};
+  a.rows_out = B * Np; a.feat_channels = (int)C; a.feat = feat2d; a.xyz = pix_xyz; a.new_xyz = points; a.nbr = knn;
+  a.n_src = nv * h * w; a.n_out = Np; a.k = (int)K; a.reduce = reduce_sum ? REDUCE_SUM : REDUCE_MAX;
+  a.s_n = s_n; a.s_c = s_c; a.s_h = s_h; a.s_w = s_w; a.hw = (int)(h * w); a.w = (int)w; a.nv = (int)nv;
+  return tc::launch<MODE_FA>(a, m, out, (a.rows_out + 31) / 32, (cudaStream_t)stream);
+}
+
+extern "C" int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const int64_t *idx, const float *dist2,
+                                                const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
+                                                const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(Cs % 8 == 0 && Cd % 8 == 0 && Cs > 0 && Cd >= 0, MVP_ERR_UNSUPPORTED,
+              "tc_fused_feature_propagation: channel counts must be multiples of 8");
+  MVP_REQUIRE(B >= 0 && Ns > 0 && Nd >= 0, MVP_ERR_INVALID_ARG, "tc_fused_feature_propagation: bad sizes");
+  tc::Chain m;
+  if (int rc = mvp_tc_to_chain(chain, (int)(Cs + Cd), MODE_FP, &m)) return rc;
+  if (B * Nd == 0) return 0;
+  MVP_REQUIRE(sparse_feat && idx && dist2 && out && (skip || Cd == 0), MVP_ERR_NULL, "tc_fused_feature_propagation: null pointer");
+  MVP_REQUIRE((((uintptr_t)sparse_feat | (uintptr_t)skip) & 15) == 0, MVP_ERR_INVALID_ARG,
+              "tc_fused_feature_propagation: features must be 16-byte aligned");
+  BuildArgs a = {};
+  a.rows_out = B * Nd; a.feat_channels = (int)Cs; a.feat = sparse_feat; a.nbr = idx; a.dist = dist2; a.skip = skip;
+  a.skip_channels = (int)Cd; a.n_src = Ns; a.n_out = Nd; a.k = 3; a.eps = eps;
+  return tc::launch<MODE_FP>(a, m, out, (a.rows_out + tc::ROWS - 1) / tc::ROWS, (cudaStream_t)stream);
+}

@@ -347,6 +347,124 @@ at::Tensor fused_feature_propagation(const at::Tensor sparse_feat, const at::Ten
   return out;
 }
 
+// ---- tensor-core (tcgen05) variants ------------------------------------------------------------------
+struct TcChain {
+  mvp_tc_chain_t c;
+  TcChain(const std::vector<at::Tensor> &w_hi, const std::vector<at::Tensor> &w_lo, const std::vector<at::Tensor> &biases,
+          const std::vector<int64_t> &ks, const std::vector<int64_t> &ns, const std::vector<int64_t> &relu,
+          int64_t out_channels, const at::Device &dev) {
+    const size_t L = w_hi.size();
+    TORCH_CHECK(L >= 1 && L <= MVP_MLP_MAX_LAYERS, "tc mlp: 1..", MVP_MLP_MAX_LAYERS, " layers");
+    TORCH_CHECK(w_lo.size() == L && biases.size() == L && ks.size() == L && ns.size() == L && relu.size() == L,
+                "tc mlp: list lengths differ");
+    c.num_layers = (int32_t)L;
+    c.out_channels = (int32_t)out_channels;
+    for (size_t l = 0; l < L; ++l) {
+      TORCH_CHECK(w_hi[l].is_cuda() && w_lo[l].is_cuda() && biases[l].is_cuda() && w_hi[l].device() == dev,
+                  "tc mlp: weights on wrong device");
+      TORCH_CHECK(w_hi[l].scalar_type() == at::kBFloat16 && w_lo[l].scalar_type() == at::kBFloat16 &&
+                      biases[l].scalar_type() == at::kFloat,
+                  "tc mlp: w_hi/w_lo must be bfloat16, bias float32");
+      TORCH_CHECK(w_hi[l].is_contiguous() && w_lo[l].is_contiguous() && biases[l].is_contiguous(), "tc mlp: contiguous weights");
+      TORCH_CHECK(w_hi[l].numel() == ks[l] * ns[l] && w_lo[l].numel() == ks[l] * ns[l] && biases[l].numel() == ns[l],
+                  "tc mlp: weight sizes do not match k x n");
+      c.k[l] = (int32_t)ks[l];
+      c.n[l] = (int32_t)ns[l];
+      c.relu[l] = (int32_t)relu[l];
+      c.w_hi[l] = w_hi[l].data_ptr();
+      c.w_lo[l] = w_lo[l].data_ptr();
+      c.bias[l] = biases[l].data_ptr<float>();
+    }
+  }
+};
+
+bool tc_chain_supported(const std::vector<int64_t> ks, const std::vector<int64_t> ns, int64_t mode) {
+  mvp_tc_chain_t c = {};
+  if (ks.empty() || ks.size() > MVP_MLP_MAX_LAYERS || ks.size() != ns.size()) return false;
+  c.num_layers = (int32_t)ks.size();
+  for (size_t l = 0; l < ks.size(); ++l) { c.k[l] = (int32_t)ks[l]; c.n[l] = (int32_t)ns[l]; }
+  return mvp_tc_chain_supported(&c, (int)mode) != 0;
+}
+
+at::Tensor tc_set_abstraction(const c10::optional<at::Tensor> feat, const at::Tensor xyz, const at::Tensor new_xyz,
+                              const at::Tensor nbr, const std::vector<at::Tensor> w_hi, const std::vector<at::Tensor> w_lo,
+                              const std::vector<at::Tensor> biases, const std::vector<int64_t> ks, const std::vector<int64_t> ns,
+                              const std::vector<int64_t> relu, int64_t out_channels) {
+  CHECK_INPUT(xyz); CHECK_INPUT(new_xyz); CHECK_INPUT(nbr);
+  CHECK_F32(xyz); CHECK_F32(new_xyz);
+  TORCH_CHECK(xyz.dim() == 3 && xyz.size(2) == 3 && new_xyz.dim() == 3 && new_xyz.size(2) == 3, "xyz/new_xyz must be (B, N, 3)");
+  TORCH_CHECK(nbr.scalar_type() == at::kLong && nbr.dim() == 3, "nbr must be int64 (B, M, K)");
+  const auto B = xyz.size(0), N = xyz.size(1), M = new_xyz.size(1), K = nbr.size(2);
+  TORCH_CHECK(new_xyz.size(0) == B && nbr.size(0) == B && nbr.size(1) == M, "tc_set_abstraction: shape mismatch");
+  int64_t C = 0;
+  const float *fp = nullptr;
+  if (feat.has_value() && feat->defined()) {
+    CHECK_INPUT((*feat)); CHECK_F32((*feat));
+    TORCH_CHECK(feat->dim() == 3 && feat->size(0) == B && feat->size(1) == N, "feat must be (B, N, C)");
+    C = feat->size(2);
+    fp = feat->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(xyz.device());
+  TcChain ch(w_hi, w_lo, biases, ks, ns, relu, out_channels, xyz.device());
+  auto out = at::empty({B, M, out_channels}, xyz.options());
+  check_rc(mvp_tc_fused_set_abstraction(fp, C, xyz.data_ptr<float>(), new_xyz.data_ptr<float>(), nbr.data_ptr<int64_t>(), B, N, M,
+                                        K, &ch.c, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
+at::Tensor tc_feature_aggregation(const at::Tensor feat2d, const at::Tensor pix_xyz, const at::Tensor points, const at::Tensor knn,
+                                  bool reduce_sum, const std::vector<at::Tensor> w_hi, const std::vector<at::Tensor> w_lo,
+                                  const std::vector<at::Tensor> biases, const std::vector<int64_t> ks, const std::vector<int64_t> ns,
+                                  const std::vector<int64_t> relu, int64_t out_channels) {
+  CHECK_CUDA(feat2d); CHECK_F32(feat2d);
+  CHECK_INPUT(pix_xyz); CHECK_INPUT(points); CHECK_INPUT(knn);
+  CHECK_F32(pix_xyz); CHECK_F32(points);
+  TORCH_CHECK(feat2d.dim() == 5, "feat2d must be (B, nv, C, h, w)");
+  const auto B = feat2d.size(0), nv = feat2d.size(1), C = feat2d.size(2), h = feat2d.size(3), w = feat2d.size(4);
+  TORCH_CHECK(feat2d.stride(0) == nv * feat2d.stride(1), "feat2d: batch and view axes must be collapsible");
+  TORCH_CHECK(pix_xyz.dim() == 3 && pix_xyz.size(0) == B && pix_xyz.size(1) == nv * h * w && pix_xyz.size(2) == 3,
+              "pix_xyz must be (B, nv*h*w, 3)");
+  TORCH_CHECK(points.dim() == 3 && points.size(0) == B && points.size(2) == 3, "points must be (B, Np, 3)");
+  TORCH_CHECK(knn.scalar_type() == at::kLong && knn.dim() == 3 && knn.size(0) == B && knn.size(1) == points.size(1),
+              "knn must be int64 (B, Np, K)");
+  c10::cuda::CUDAGuard guard(feat2d.device());
+  TcChain ch(w_hi, w_lo, biases, ks, ns, relu, out_channels, feat2d.device());
+  auto out = at::empty({B, points.size(1), out_channels}, points.options());
+  check_rc(mvp_tc_fused_feature_aggregation(feat2d.data_ptr<float>(), feat2d.stride(1), feat2d.stride(2), feat2d.stride(3),
+                                            feat2d.stride(4), C, nv, h, w, pix_xyz.data_ptr<float>(), points.data_ptr<float>(),
+                                            knn.data_ptr<int64_t>(), B, points.size(1), knn.size(2), reduce_sum ? 1 : 0, &ch.c,
+                                            out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
+at::Tensor tc_feature_propagation(const at::Tensor sparse_feat, const at::Tensor idx, const at::Tensor dist2,
+                                  const c10::optional<at::Tensor> skip, double eps, const std::vector<at::Tensor> w_hi,
+                                  const std::vector<at::Tensor> w_lo, const std::vector<at::Tensor> biases,
+                                  const std::vector<int64_t> ks, const std::vector<int64_t> ns, const std::vector<int64_t> relu,
+                                  int64_t out_channels) {
+  CHECK_INPUT(sparse_feat); CHECK_INPUT(idx); CHECK_INPUT(dist2);
+  CHECK_F32(sparse_feat); CHECK_F32(dist2);
+  TORCH_CHECK(sparse_feat.dim() == 3 && idx.dim() == 3 && dist2.dim() == 3 && idx.size(2) == 3 && dist2.size(2) == 3,
+              "tc_feature_propagation: sparse_feat (B,Ns,Cs), idx/dist2 (B,Nd,3)");
+  TORCH_CHECK(idx.scalar_type() == at::kLong, "idx must be int64");
+  const auto B = sparse_feat.size(0), Ns = sparse_feat.size(1), Cs = sparse_feat.size(2), Nd = idx.size(1);
+  TORCH_CHECK(idx.size(0) == B && dist2.size(0) == B && dist2.size(1) == Nd, "tc_feature_propagation: shape mismatch");
+  int64_t Cd = 0;
+  const float *sp = nullptr;
+  if (skip.has_value() && skip->defined()) {
+    CHECK_INPUT((*skip)); CHECK_F32((*skip));
+    TORCH_CHECK(skip->dim() == 3 && skip->size(0) == B && skip->size(1) == Nd, "skip must be (B, Nd, Cd)");
+    Cd = skip->size(2);
+    sp = skip->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(sparse_feat.device());
+  TcChain ch(w_hi, w_lo, biases, ks, ns, relu, out_channels, sparse_feat.device());
+  auto out = at::empty({B, Nd, out_channels}, sparse_feat.options());
+  check_rc(mvp_tc_fused_feature_propagation(sparse_feat.data_ptr<float>(), Cs, idx.data_ptr<int64_t>(), dist2.data_ptr<float>(), sp,
+                                            Cd, B, Ns, Nd, (float)eps, &ch.c, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
 int64_t index_errors_fetch_and_clear() {
   uint64_t n = 0;
   check_rc(mvp_index_errors_fetch_and_clear(cur_stream(), &n));
@@ -381,4 +499,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("set_abstraction", &fused_set_abstraction, "gather + MLP + max (CUDA)");
   fz.def("feature_aggregation", &fused_feature_aggregation, "pixel gather + relation + MLP + sum/max (CUDA)");
   fz.def("feature_propagation", &fused_feature_propagation, "3-NN interpolate + concat + MLP (CUDA)");
+  fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
+  fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
+  fz.def("tc_feature_aggregation", &tc_feature_aggregation, "pixel gather + relation + MLP (tcgen05) + sum/max");
+  fz.def("tc_feature_propagation", &tc_feature_propagation, "3-NN interpolate + concat + MLP (tcgen05)");
 }

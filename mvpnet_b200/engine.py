@@ -19,6 +19,7 @@ is no eager/CPU fallback inside the fused path; unsupported module configuration
 op-by-op CUDA composition in modules.py (still this package's kernels).
 """
 import contextlib
+import os
 
 import torch
 from torch import nn
@@ -111,6 +112,61 @@ class Chain:
         return self.wts, self.biases, self.relu, self.out_channels
 
 
+class TcChain:
+    """The same chain packed for the tcgen05 kernels (csrc/tc_mlp.cu): every fp32 weight split into
+    bf16 hi + bf16 lo, K padded to 16, N padded to 16, stored per 256-wide block of output channels as
+    [K/8][nb][8] (the kernel's shared-memory operand order), bias fp32."""
+
+    def __init__(self, layers, cin_true, device):
+        self.w_hi, self.w_lo, self.biases, self.ks, self.ns, self.relu = [], [], [], [], [], []
+        k_pad = _round_up(cin_true, 16)
+        for conv, bn, relu in layers:
+            w, b = _fold(conv, bn)
+            cout, cin = w.shape
+            n_pad = _round_up(cout, 16)
+            wp = torch.zeros(n_pad, k_pad, dtype=torch.float64, device=w.device)
+            wp[:cout, :cin] = w
+            wp = wp.float()
+            hi = wp.bfloat16()
+            lo = (wp - hi.float()).bfloat16()
+            self.w_hi.append(self._arrange(hi, n_pad, k_pad).to(device))
+            self.w_lo.append(self._arrange(lo, n_pad, k_pad).to(device))
+            bias = torch.zeros(n_pad, dtype=torch.float64, device=w.device)
+            bias[:cout] = b
+            self.biases.append(bias.float().contiguous().to(device))
+            self.ks.append(k_pad)
+            self.ns.append(n_pad)
+            self.relu.append(1 if relu else 0)
+            k_pad = n_pad
+        self.out_channels = layers[-1][0].out_channels
+
+    @staticmethod
+    def _arrange(x, n_pad, k_pad):
+        blocks = []
+        for n0 in range(0, n_pad, 256):
+            nb = min(256, n_pad - n0)
+            blocks.append(x[n0:n0 + nb].reshape(nb, k_pad // 8, 8).permute(1, 0, 2).contiguous().reshape(-1))
+        return torch.cat(blocks).contiguous()
+
+    def args(self):
+        return self.w_hi, self.w_lo, self.biases, self.ks, self.ns, self.relu, self.out_channels
+
+
+# 'tc'  : tcgen05 tensor-core kernels where the chain fits (default), fp32 SIMT kernels elsewhere
+# 'simt': fp32 SIMT kernels everywhere (cross-check / fallback)
+MLP_BACKEND = os.environ.get('MVPNET_B200_MLP', 'tc')
+_MODE_SA, _MODE_FA, _MODE_FP = 0, 1, 2
+
+
+def _make_chain(layers, cin_true, device, mode, channels_ok):
+    """Pick the tensor-core packing when enabled, channel counts are multiples of 8 and the tile fits."""
+    if MLP_BACKEND == 'tc' and channels_ok:
+        tc = TcChain(layers, cin_true, device)
+        if load_ext().fused_cuda.tc_chain_supported(tc.ks, tc.ns, mode):
+            return tc
+    return Chain(layers, cin_true, device)
+
+
 def _mlp_layers(shared_mlp):
     return [(m.conv, m.bn, m.relu is not None) for m in shared_mlp]
 
@@ -149,12 +205,12 @@ def feature_aggregation(fa, feat2d, image_xyz, knn_indices, points, point_major_
     if fa.mlp is None or not fa.use_relation or knn_indices.size(2) > 4:
         raise RuntimeError('fused feature_aggregation supports use_relation=True, an MLP and k <= 4')
     b, nv, c, h, w = feat2d.shape
-    chain = _cached(fa, 'fa', lambda: Chain(_mlp_layers(fa.mlp), c + 4, feat2d.device))
+    chain = _cached(fa, 'fa' + MLP_BACKEND, lambda: _make_chain(_mlp_layers(fa.mlp), c + 4, feat2d.device, _MODE_FA, c % 8 == 0))
     pix = image_xyz.reshape(b, nv * h * w, 3).contiguous()
     pts = points.transpose(1, 2).contiguous()
+    fn = ext.fused_cuda.tc_feature_aggregation if isinstance(chain, TcChain) else ext.fused_cuda.feature_aggregation
     with _stage('feature_aggregation'):
-        out = ext.fused_cuda.feature_aggregation(feat2d, pix, pts, knn_indices.contiguous(),
-                                                 fa.reduction_name == 'sum', *chain.args())
+        out = fn(feat2d, pix, pts, knn_indices.contiguous(), fa.reduction_name == 'sum', *chain.args())
     return out if point_major_out else out.transpose(1, 2).contiguous()
 
 
@@ -198,13 +254,16 @@ def pn2_geometry(net, xyz_pm):
 def _pn2_chains(net, device):
     sa = []
     for m in net.sa_modules:
-        sa.append(Chain(_mlp_layers(m.mlp), m.in_channels, device))
+        sa.append(_make_chain(_mlp_layers(m.mlp), m.in_channels, device, _MODE_SA, (m.in_channels - 3) % 8 == 0))
     fp = []
     for i, m in enumerate(net.fp_modules):
         layers = _mlp_layers(m.mlp)
         if i == len(net.fp_modules) - 1:           # segmentation head rides on the last chain
             layers = layers + _mlp_layers(net.mlp_seg) + [(net.seg_logit, None, False)]
-        fp.append(Chain(layers, m.in_channels, device))
+        # interpolated and skip channel counts must both be multiples of 8 for the 8-channel operand units
+        prev = net.fp_modules[i - 1].out_channels if i > 0 else net.sa_modules[-1].out_channels
+        ok = prev % 8 == 0 and (m.in_channels - prev) % 8 == 0
+        fp.append(_make_chain(layers, m.in_channels, device, _MODE_FP, ok))
     return sa, fp
 
 
@@ -212,21 +271,23 @@ def pn2_features(net, geo, feature_pm):
     """The feature side of PN2SSG.forward on precomputed geometry.  feature_pm (B, N, C) or None.
     Returns seg_logit (B, num_classes, N)."""
     ext = load_ext()
-    sa_chains, fp_chains = _cached(net, 'pn2', lambda: _pn2_chains(net, geo['xyz'][0].device))
-    if len(fp_chains[-1].wts) > 6:
+    sa_chains, fp_chains = _cached(net, 'pn2' + MLP_BACKEND, lambda: _pn2_chains(net, geo['xyz'][0].device))
+    if len(fp_chains[-1].relu) > 6:
         raise RuntimeError('fused PN2SSG: last FP chain + head exceeds 6 layers')
     feats = [None]
     f = feature_pm
     for i, sa in enumerate(net.sa_modules):
         src = f if (f is not None) else None
+        fn = ext.fused_cuda.tc_set_abstraction if isinstance(sa_chains[i], TcChain) else ext.fused_cuda.set_abstraction
         with _stage('set_abstraction%d' % (i + 1)):
-            f = ext.fused_cuda.set_abstraction(src, geo['xyz'][i], geo['xyz'][i + 1], geo['nbr'][i], *sa_chains[i].args())
+            f = fn(src, geo['xyz'][i], geo['xyz'][i + 1], geo['nbr'][i], *sa_chains[i].args())
         feats.append(f)
     x = feats[-1]
     for i, fp in enumerate(net.fp_modules):
         idx, d2 = geo['knn'][i]
+        fn = ext.fused_cuda.tc_feature_propagation if isinstance(fp_chains[i], TcChain) else ext.fused_cuda.feature_propagation
         with _stage('feature_propagation%d' % (i + 1)):
-            x = ext.fused_cuda.feature_propagation(x, idx, d2, feats[-2 - i], fp.interpolator._eps, *fp_chains[i].args())
+            x = fn(x, idx, d2, feats[-2 - i], fp.interpolator._eps, *fp_chains[i].args())
     return x.transpose(1, 2).contiguous()
 
 
