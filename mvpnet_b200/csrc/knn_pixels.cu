@@ -22,6 +22,10 @@ constexpr int KP_WARPS = 8;
 constexpr int KP_TILE = 1792;  // pixels per shared-memory tile: 42 KB xyz + 1.75 KB mask (static smem <= 48 KB)
 constexpr int KP_QPW = 4;
 constexpr int KP_CELL_CAP = 1 << 18;  // max grid cells per cloud
+#ifndef MVP_KP_CELL_SCALE
+#define MVP_KP_CELL_SCALE 2.0
+#endif
+constexpr double KP_CELL_SCALE = MVP_KP_CELL_SCALE;  // cell edge in units of the mean pixel spacing (pixels lie on surfaces: most cells are empty)
 
 __device__ __forceinline__ double sqdist3_nofma(double kx, double ky, double kz, double qx, double qy, double qz) {
   const double dx = __dsub_rn(kx, qx), dy = __dsub_rn(ky, qy), dz = __dsub_rn(kz, qz);
@@ -174,7 +178,7 @@ kp_bbox_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ mask,
       double ext[3];
       for (int a = 0; a < 3; ++a) ext[a] = fmax(hi[a] - lo[a], 1e-6);
       // cell edge ~ mean spacing of the pixels if they filled the box; grown until the grid fits the cap
-      double s = cbrt(ext[0] * ext[1] * ext[2] / (double)min(cnt, KP_CELL_CAP / 2));
+      double s = KP_CELL_SCALE * cbrt(ext[0] * ext[1] * ext[2] / (double)min(cnt, KP_CELL_CAP / 2));
       s = fmax(s, 1e-6);
       int gx, gy, gz;
       for (;;) {
@@ -324,9 +328,19 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
       }
       kth = d;
     }
-    // every pixel outside shells 0..r lies farther than r * s from the query
-    const double bound = __dmul_rn((double)r, g.s);
-    if (kth < __dmul_rn(__dmul_rn(bound, bound), 1.0 - 1e-9)) break;
+    // Every pixel outside the visited cube [c-r, c+r]^3 lies beyond one of the cube's faces that still has
+    // cells behind it; its distance is at least the distance from the query to that face plane.
+    double bound = Inf<double>::v();
+    {
+      const double qv[3] = {qx, qy, qz}, ov[3] = {g.ox, g.oy, g.oz};
+      const int cv[3] = {cx, cy, cz}, gv[3] = {g.gx, g.gy, g.gz};
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (cv[a] - r > 0) bound = fmin(bound, __dsub_rn(qv[a], __dadd_rn(ov[a], __dmul_rn((double)(cv[a] - r), g.s))));
+        if (cv[a] + r + 1 < gv[a]) bound = fmin(bound, __dsub_rn(__dadd_rn(ov[a], __dmul_rn((double)(cv[a] + r + 1), g.s)), qv[a]));
+      }
+    }
+    if (bound > 0.0 && kth < __dmul_rn(__dmul_rn(bound, bound), 1.0 - 1e-9)) break;
   }
 
   for (int j = 0; j < k; ++j) {

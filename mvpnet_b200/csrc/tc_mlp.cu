@@ -141,112 +141,164 @@ __device__ __forceinline__ void load8(const float *p, bool ok, float (&v)[8]) {
   }
 }
 
-// ---- row builders (one warp per row, lanes over 8-channel groups) -------------------------------
-__device__ __forceinline__ void build_sa(const BuildArgs &a, unsigned char *a_hi, unsigned char *a_lo, int kblocks, long long tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = a.feat_channels, cb = C >> 3;
-  for (int r = warp; r < ROWS; r += THREADS / 32) {
-    const long long gid = tile * 4 + (r >> 5);
-    long long j = -1, b = 0;
-    if (gid < a.rows_out) { b = gid / a.n_out; j = a.nbr[gid * 32 + (r & 31)]; }
-    const bool ok = j >= 0 && j < a.n_src;
-    const float *src = a.feat + ((size_t)b * a.n_src + (ok ? j : 0)) * C;
-    for (int kb = lane; kb < kblocks; kb += 32) {
-      float v[8];
-      if (kb < cb) {
-        load8(src + kb * 8, ok, v);
-      } else {
+// ---- row builders ---------------------------------------------------------------------------------
+// Phase A: one thread per row resolves the row's source address(es) and its relation / weight scalars into
+// shared memory (coalesced index reads).  Phase B: the tile is cut into (row, 8-channel) units, row-fastest
+// so that consecutive lanes write consecutive 16-byte slots of one K-slab (conflict-free); every thread
+// issues the global loads of several units before it converts and stores any of them, which is what hides
+// the gather latency (the two dependent loads index -> row used to be serialised per row).
+struct Aux {                 // per-tile scratch in shared memory
+  long long src[ROWS * 3];   // element offset of the source row(s); < 0 = no source (zero row)
+  float w[ROWS * 3];         // FP: interpolation weights
+  float rel[ROWS * 4];       // SA: xyz - centroid; FA: dx, dy, dz, |d|^2
+};
+
+__device__ __forceinline__ void zero8(float (&v)[8]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        if (kb == cb && ok) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-            v[i] = __fsub_rn(__ldg(a.xyz + ((size_t)b * a.n_src + j) * 3 + i), __ldg(a.new_xyz + gid * 3 + i));
-        }
-      }
-      store8(a_hi, a_lo, r, kb, v);
-    }
-  }
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
 }
 
-__device__ __forceinline__ void build_fa(const BuildArgs &a, unsigned char *a_hi, unsigned char *a_lo, int kblocks, long long tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = a.feat_channels, cb = C >> 3;
-  for (int r = warp; r < ROWS; r += THREADS / 32) {
-    const int i = r >> 5, p = r & 31;
-    const long long pid = tile * 32 + p;
-    long long j = -1, b = 0;
-    if (pid < a.rows_out && i < a.k) { b = pid / a.n_out; j = a.nbr[pid * a.k + i]; }
-    const bool ok = j >= 0 && j < a.n_src;
-    const long long jj = ok ? j : 0;
-    const int v_ = (int)(jj / a.hw), pix = (int)(jj - (long long)v_ * a.hw);
-    const int y = pix / a.w, x = pix - y * a.w;
-    const float *src = a.feat + ((size_t)b * a.nv + v_) * a.s_n + (size_t)y * a.s_h + (size_t)x * a.s_w;
-    for (int kb = lane; kb < kblocks; kb += 32) {
-      float v[8];
+template <int MODE>
+__device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned char *a_hi, unsigned char *a_lo, int kblocks,
+                                           long long tile) {
+  const int tid = threadIdx.x;
+  // ---------------- phase A
+  if (tid < ROWS) {
+    const int r = tid;
+    if (MODE == MODE_SA) {
+      const long long gid = tile * 4 + (r >> 5);
+      long long j = -1, b = 0;
+      if (gid < a.rows_out) { b = gid / a.n_out; j = a.nbr[gid * 32 + (r & 31)]; }
+      const bool ok = j >= 0 && j < a.n_src;
+      x.src[r] = ok ? b * a.n_src + j : -1;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = 0.f;
-      if (kb < cb) {
-        if (a.s_c == 1) load8(src + kb * 8, ok, v);
-        else if (ok) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) v[c] = __ldg(src + (size_t)(kb * 8 + c) * a.s_c);
-        }
-      } else if (kb == cb && ok) {
+      for (int i = 0; i < 3; ++i)
+        x.rel[r * 4 + i] = ok ? __fsub_rn(__ldg(a.xyz + ((size_t)b * a.n_src + j) * 3 + i), __ldg(a.new_xyz + gid * 3 + i)) : 0.f;
+      x.rel[r * 4 + 3] = 0.f;
+    } else if (MODE == MODE_FA) {
+      const int i = r >> 5, p = r & 31;
+      const long long pid = tile * 32 + p;
+      long long j = -1, b = 0;
+      if (pid < a.rows_out && i < a.k) { b = pid / a.n_out; j = a.nbr[pid * a.k + i]; }
+      const bool ok = j >= 0 && j < a.n_src;
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      long long off = -1;
+      if (ok) {
+        const int v_ = (int)(j / a.hw), pix = (int)(j - (long long)v_ * a.hw);
+        const int y = pix / a.w, xx = pix - y * a.w;
+        off = ((long long)b * a.nv + v_) * a.s_n + (long long)y * a.s_h + (long long)xx * a.s_w;
         const float *s = a.xyz + ((size_t)b * a.n_src + j) * 3;
         const float *t = a.new_xyz + pid * 3;
-        v[0] = __fsub_rn(__ldg(s), __ldg(t)); v[1] = __fsub_rn(__ldg(s + 1), __ldg(t + 1)); v[2] = __fsub_rn(__ldg(s + 2), __ldg(t + 2));
-        v[3] = __fadd_rn(__fadd_rn(__fmul_rn(v[0], v[0]), __fmul_rn(v[1], v[1])), __fmul_rn(v[2], v[2]));
+        d[0] = __fsub_rn(__ldg(s), __ldg(t)); d[1] = __fsub_rn(__ldg(s + 1), __ldg(t + 1)); d[2] = __fsub_rn(__ldg(s + 2), __ldg(t + 2));
+        d[3] = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
       }
-      store8(a_hi, a_lo, r, kb, v);
+      x.src[r] = off;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) x.rel[r * 4 + c] = d[c];
+    } else {
+      const long long pid = tile * ROWS + r;
+      const bool live = pid < a.rows_out;
+      const long long b = live ? pid / a.n_out : 0;
+      float w[3] = {0.f, 0.f, 0.f};
+      long long j[3] = {-1, -1, -1};
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          j[k] = a.nbr[pid * 3 + k];
+          w[k] = __fdiv_rn(1.0f, fmaxf(__ldg(a.dist + pid * 3 + k), a.eps));
+          if (j[k] < 0 || j[k] >= a.n_src) { j[k] = -1; w[k] = 0.f; }
+        }
+        const float norm = __fadd_rn(__fadd_rn(w[0], w[1]), w[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = __fdiv_rn(w[k], norm);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { x.src[r * 3 + k] = j[k] >= 0 ? b * a.n_src + j[k] : -1; x.w[r * 3 + k] = w[k]; }
     }
   }
-}
-
-__device__ __forceinline__ void build_fp(const BuildArgs &a, unsigned char *a_hi, unsigned char *a_lo, int kblocks, long long tile) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Cs = a.feat_channels, Cd = a.skip_channels, sb = Cs >> 3, db = Cd >> 3;
-  for (int r = warp; r < ROWS; r += THREADS / 32) {
-    const long long pid = tile * ROWS + r;
-    const bool live = pid < a.rows_out;
-    const long long b = live ? pid / a.n_out : 0;
-    float w[3] = {0.f, 0.f, 0.f};
-    long long j[3] = {0, 0, 0};
-    if (live) {
+  __syncthreads();
+  // ---------------- phase B: a warp covers 8 rows x 4 K-slabs per step: lane = (slab sub-index << 3) | row sub-index.
+  // Loads: 8 rows x 128 contiguous bytes (whole lines); stores: per slab 8 rows x 16 B = 128 contiguous bytes
+  // (all 32 banks, conflict-free).
+  const int warp = tid >> 5, lane = tid & 31, rs = lane & 7, ks = lane >> 3;
+  const int nblk = 16 * ((kblocks + 3) >> 2);
+  if (MODE == MODE_FP) {
+    const int Cs = a.feat_channels, Cd = a.skip_channels, sb = Cs >> 3, db = Cd >> 3;
+    constexpr int U = 2;
+    for (int wb0 = warp; wb0 < nblk; wb0 += (THREADS / 32) * U) {
+      float v0[U][8], v1[U][8], v2[U][8];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        j[k] = a.nbr[pid * 3 + k];
-        w[k] = __fdiv_rn(1.0f, fmaxf(__ldg(a.dist + pid * 3 + k), a.eps));
-        if (j[k] < 0 || j[k] >= a.n_src) { j[k] = 0; w[k] = 0.f; }
+      for (int i = 0; i < U; ++i) {
+        const int wb = wb0 + i * (THREADS / 32);
+        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
+        zero8(v0[i]); zero8(v1[i]); zero8(v2[i]);
+        if (wb < nblk && kb < kblocks) {
+          if (kb < sb) {
+            const long long s0 = x.src[r * 3], s1 = x.src[r * 3 + 1], s2 = x.src[r * 3 + 2];
+            load8(a.feat + (size_t)(s0 < 0 ? 0 : s0) * Cs + kb * 8, s0 >= 0, v0[i]);
+            load8(a.feat + (size_t)(s1 < 0 ? 0 : s1) * Cs + kb * 8, s1 >= 0, v1[i]);
+            load8(a.feat + (size_t)(s2 < 0 ? 0 : s2) * Cs + kb * 8, s2 >= 0, v2[i]);
+          } else if (kb < sb + db) {
+            const long long pid = tile * ROWS + r;
+            load8(a.skip + (size_t)(pid < a.rows_out ? pid : 0) * Cd + (kb - sb) * 8, pid < a.rows_out, v0[i]);
+          }
+        }
       }
-      const float norm = __fadd_rn(__fadd_rn(w[0], w[1]), w[2]);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) w[k] = __fdiv_rn(w[k], norm);
+      for (int i = 0; i < U; ++i) {
+        const int wb = wb0 + i * (THREADS / 32);
+        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
+        if (wb < nblk && kb < kblocks) {
+          if (kb < sb) {
+            const float w0 = x.w[r * 3], w1 = x.w[r * 3 + 1], w2 = x.w[r * 3 + 2];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)  // interpolate_kernel.cu:54-61 accumulation order
+              v0[i][c] = __fmaf_rn(v2[i][c], w2, __fmaf_rn(v1[i][c], w1, __fmul_rn(v0[i][c], w0)));
+          }
+          store8(a_hi, a_lo, r, kb, v0[i]);
+        }
+      }
     }
-    const float *s0 = a.feat + ((size_t)b * a.n_src + j[0]) * Cs;
-    const float *s1 = a.feat + ((size_t)b * a.n_src + j[1]) * Cs;
-    const float *s2 = a.feat + ((size_t)b * a.n_src + j[2]) * Cs;
-    for (int kb = lane; kb < kblocks; kb += 32) {
-      float v[8];
-      if (kb < sb) {
-        float v0[8], v1[8], v2[8];
-        load8(s0 + kb * 8, live, v0); load8(s1 + kb * 8, live, v1); load8(s2 + kb * 8, live, v2);
+  } else {
+    const int cb = a.feat_channels >> 3;
+    constexpr int U = 3;
+    for (int wb0 = warp; wb0 < nblk; wb0 += (THREADS / 32) * U) {
+      float v[U][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = __fmaf_rn(v2[c], w[2], __fmaf_rn(v1[c], w[1], __fmul_rn(v0[c], w[0])));
-      } else if (kb < sb + db) {
-        load8(a.skip + (size_t)pid * Cd + (kb - sb) * 8, live, v);
-      } else {
+      for (int i = 0; i < U; ++i) {
+        const int wb = wb0 + i * (THREADS / 32);
+        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
+        zero8(v[i]);
+        if (wb < nblk && kb < kblocks) {
+          const long long s0 = x.src[r];
+          if (kb < cb) {
+            if (MODE == MODE_SA) {
+              load8(a.feat + (size_t)(s0 < 0 ? 0 : s0) * a.feat_channels + kb * 8, s0 >= 0, v[i]);
+            } else if (a.s_c == 1) {
+              load8(a.feat + (s0 < 0 ? 0 : s0) + kb * 8, s0 >= 0, v[i]);
+            } else if (s0 >= 0) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = 0.f;
+              for (int c = 0; c < 8; ++c) v[i][c] = __ldg(a.feat + s0 + (long long)(kb * 8 + c) * a.s_c);
+            }
+          } else if (kb == cb) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[i][c] = x.rel[r * 4 + c];
+          }
+        }
       }
-      store8(a_hi, a_lo, r, kb, v);
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const int wb = wb0 + i * (THREADS / 32);
+        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
+        if (wb < nblk && kb < kblocks) store8(a_hi, a_lo, r, kb, v[i]);
+      }
     }
   }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 4)
 tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, long long num_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -254,8 +306,10 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
   const size_t stage_half = (size_t)(m.kc >> 3) * m.nbmax * 16;  // one of {hi, lo} of one ring stage
   unsigned char *a_hi = smem, *a_lo = smem + a_bytes;
   unsigned char *ring = smem + 2 * a_bytes;                      // [stage][hi|lo]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + 4 * stage_half);
+  const size_t ring_bytes = 4 * stage_half > sizeof(Aux) ? 4 * stage_half : sizeof(Aux);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + ((ring_bytes + 127) & ~(size_t)127));
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+  Aux &aux = *reinterpret_cast<Aux *>(ring);   // the ring is idle while a tile is being built: scratch aliases it
   const uint32_t bar_w0 = smem_u32(bars), bar_w1 = smem_u32(bars + 1), bar_done = smem_u32(bars + 2);
 
   if (tid == 0) {
@@ -272,9 +326,7 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
   uint32_t done_phase = 0;
 
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    if (MODE == MODE_SA) build_sa(a, a_hi, a_lo, m.k[0] >> 3, tile);
-    else if (MODE == MODE_FA) build_fa(a, a_hi, a_lo, m.k[0] >> 3, tile);
-    else build_fp(a, a_hi, a_lo, m.k[0] >> 3, tile);
+    build_rows<MODE>(a, aux, a_hi, a_lo, m.k[0] >> 3, tile);
     fence_proxy_async();
     __syncthreads();
 
@@ -396,7 +448,8 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
 }
 
 static size_t smem_bytes(const Chain &m) {
-  return (size_t)(m.kmax >> 3) * SLAB * 2 + (size_t)4 * (m.kc >> 3) * m.nbmax * 16 + 64;
+  const size_t ring = (size_t)4 * (m.kc >> 3) * m.nbmax * 16;
+  return (size_t)(m.kmax >> 3) * SLAB * 2 + (((ring > sizeof(Aux) ? ring : sizeof(Aux)) + 127) & ~(size_t)127) + 64;
 }
 
 // fills the derived fields; returns false when the chain does not fit this kernel
@@ -425,11 +478,11 @@ static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cuda
   const size_t smem = smem_bytes(m);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_fused_mlp: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
-  // persistent: as many CTAs as fit (shared memory and TMEM columns bound the residency)
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  // persistent: as many CTAs as are resident (registers / shared memory from the occupancy API, TMEM columns here)
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
   if (per_sm * m.tmem_cols > 512) per_sm = 512 / m.tmem_cols;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
   long long grid = (long long)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, THREADS, smem, stream>>>(a, m, out, tiles);
