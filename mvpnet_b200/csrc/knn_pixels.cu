@@ -14,6 +14,8 @@
 //     lanes stream coalesced ranges.  After shell r every unvisited pixel is farther than r * cell, so
 //     the walk stops as soon as the k-th best squared distance is below (r * cell)^2 — the result is
 //     EXACTLY the exhaustive one (same arithmetic, same tie rule), at ~1/50 of the evaluations.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvp {
@@ -139,7 +141,7 @@ __device__ __forceinline__ int cell_coord(double p, double o, double inv_s, int 
 
 // bbox of the valid pixels + grid parameters; one CTA per cloud
 __global__ void __launch_bounds__(1024)
-kp_bbox_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ mask, int P, KpGrid *__restrict__ grids) {
+kp_bbox_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ mask, int P, KpGrid *__restrict__ grids, double cell_scale) {
   __shared__ double s_lo[3][32], s_hi[3][32];
   __shared__ int s_cnt[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -178,7 +180,7 @@ kp_bbox_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ mask,
       double ext[3];
       for (int a = 0; a < 3; ++a) ext[a] = fmax(hi[a] - lo[a], 1e-6);
       // cell edge ~ mean spacing of the pixels if they filled the box; grown until the grid fits the cap
-      double s = KP_CELL_SCALE * cbrt(ext[0] * ext[1] * ext[2] / (double)min(cnt, KP_CELL_CAP / 2));
+      double s = cell_scale * cbrt(ext[0] * ext[1] * ext[2] / (double)min(cnt, KP_CELL_CAP / 2));
       s = fmax(s, 1e-6);
       int gx, gy, gz;
       for (;;) {
@@ -401,7 +403,8 @@ extern "C" int mvp_knn_pixels(const double *query, const double *pix_xyz, const 
   int *sorted_id = (int *)w;
   cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int) * (size_t)B * (KP_CELL_CAP + 1), stream);
   if (e != cudaSuccess) { set_error("knn_pixels: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
-  kp_bbox_kernel<<<(unsigned)B, 1024, 0, stream>>>(pix_xyz, mask, (int)P, grids);
+  static const double cell_scale = [] { const char *e = getenv("MVPNET_B200_KP_CELL_SCALE"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : KP_CELL_SCALE; }();
+  kp_bbox_kernel<<<(unsigned)B, 1024, 0, stream>>>(pix_xyz, mask, (int)P, grids, cell_scale);
   dim3 pgrid((unsigned)((P + 255) / 256), (unsigned)B);
   kp_count_kernel<<<pgrid, 256, 0, stream>>>(pix_xyz, mask, (int)P, grids, cells);
   kp_scan_kernel<<<(unsigned)B, 1024, 0, stream>>>(grids, cells);

@@ -42,6 +42,11 @@ struct Chain {
   int kmax;               // max k over layers
   int nbmax;              // max N-block width over layers (<= 256)
   int tmem_cols;          // power of two >= max n, >= 32
+  int resident;           // 1: all weights live in shared memory for the whole kernel (narrow chains)
+  int stages;             // ring depth when not resident (2..4)
+  int res_off[MAX_LAYERS];  // resident mode: byte offset of layer l's hi block (lo follows at + k*n*2)
+  int res_bytes;
+  int panel;              // K elements of the first layer built per pass (== k[0] unless the row is too wide for shared memory)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -63,6 +68,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA unit, no tensor map); completion is signalled on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -159,11 +173,11 @@ __device__ __forceinline__ void zero8(float (&v)[8]) {
 }
 
 template <int MODE>
-__device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned char *a_hi, unsigned char *a_lo, int kblocks,
-                                           long long tile) {
+__device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned char *a_hi, unsigned char *a_lo, int kb_begin,
+                                           int kblocks, long long tile) {
   const int tid = threadIdx.x;
-  // ---------------- phase A
-  if (tid < ROWS) {
+  // ---------------- phase A (once per tile: the scratch survives the K panels of a wide first layer)
+  if (kb_begin == 0 && tid < ROWS) {
     const int r = tid;
     if (MODE == MODE_SA) {
       const long long gid = tile * 4 + (r >> 5);
@@ -230,9 +244,9 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         const int wb = wb0 + i * (THREADS / 32);
-        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
+        const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
         zero8(v0[i]); zero8(v1[i]); zero8(v2[i]);
-        if (wb < nblk && kb < kblocks) {
+        if (wb < nblk && kl < kblocks) {
           if (kb < sb) {
             const long long s0 = x.src[r * 3], s1 = x.src[r * 3 + 1], s2 = x.src[r * 3 + 2];
             load8(a.feat + (size_t)(s0 < 0 ? 0 : s0) * Cs + kb * 8, s0 >= 0, v0[i]);
@@ -247,15 +261,15 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         const int wb = wb0 + i * (THREADS / 32);
-        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
-        if (wb < nblk && kb < kblocks) {
+        const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
+        if (wb < nblk && kl < kblocks) {
           if (kb < sb) {
             const float w0 = x.w[r * 3], w1 = x.w[r * 3 + 1], w2 = x.w[r * 3 + 2];
 #pragma unroll
             for (int c = 0; c < 8; ++c)  // interpolate_kernel.cu:54-61 accumulation order
               v0[i][c] = __fmaf_rn(v2[i][c], w2, __fmaf_rn(v1[i][c], w1, __fmul_rn(v0[i][c], w0)));
           }
-          store8(a_hi, a_lo, r, kb, v0[i]);
+          store8(a_hi, a_lo, r, kl, v0[i]);
         }
       }
     }
@@ -267,9 +281,9 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         const int wb = wb0 + i * (THREADS / 32);
-        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
+        const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
         zero8(v[i]);
-        if (wb < nblk && kb < kblocks) {
+        if (wb < nblk && kl < kblocks) {
           const long long s0 = x.src[r];
           if (kb < cb) {
             if (MODE == MODE_SA) {
@@ -289,91 +303,169 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         const int wb = wb0 + i * (THREADS / 32);
-        const int r = (wb & 15) * 8 + rs, kb = (wb >> 4) * 4 + ks;
-        if (wb < nblk && kb < kblocks) store8(a_hi, a_lo, r, kb, v[i]);
+        const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
+        if (wb < nblk && kl < kblocks) store8(a_hi, a_lo, r, kl, v[i]);
       }
     }
   }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
+constexpr int MAX_STAGES = 4;
+
+__device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t nb,
+                                            uint32_t idesc, bool first) {
+  const uint64_t ah = make_desc(a_hi, SLAB, 128), al = make_desc(a_lo, SLAB, 128);
+  const uint64_t wh = make_desc(w_hi, nb * 16, 128), wl = make_desc(w_lo, nb * 16, 128);
+  umma_bf16(d_tmem, ah, wh, idesc, first ? 0u : 1u);
+  umma_bf16(d_tmem, ah, wl, idesc, 1u);
+  umma_bf16(d_tmem, al, wh, idesc, 1u);
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, 3)
 tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, long long num_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t a_bytes = (size_t)(m.kmax >> 3) * SLAB;
   const size_t stage_half = (size_t)(m.kc >> 3) * m.nbmax * 16;  // one of {hi, lo} of one ring stage
   unsigned char *a_hi = smem, *a_lo = smem + a_bytes;
-  unsigned char *ring = smem + 2 * a_bytes;                      // [stage][hi|lo]
-  const size_t ring_bytes = 4 * stage_half > sizeof(Aux) ? 4 * stage_half : sizeof(Aux);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(ring + ((ring_bytes + 127) & ~(size_t)127));
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
-  Aux &aux = *reinterpret_cast<Aux *>(ring);   // the ring is idle while a tile is being built: scratch aliases it
-  const uint32_t bar_w0 = smem_u32(bars), bar_w1 = smem_u32(bars + 1), bar_done = smem_u32(bars + 2);
+  unsigned char *wreg = smem + 2 * a_bytes;  // resident weights, or the ring [stage][hi|lo]
+  const size_t wreg_bytes = m.resident ? (size_t)m.res_bytes : (size_t)m.stages * 2 * stage_half;
+  Aux &aux = *reinterpret_cast<Aux *>(wreg + ((wreg_bytes + 127) & ~(size_t)127));   // build scratch
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(&aux) + ((sizeof(Aux) + 127) & ~(size_t)127));
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
+  const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + MAX_STAGES), bar_done = smem_u32(bars + 2 * MAX_STAGES);
 
   if (tid == 0) {
-    mbar_init(bar_w0, 1); mbar_init(bar_w1, 1); mbar_init(bar_done, 1);
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_empty0 + 8 * s, 1); }
+    mbar_init(bar_done, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)m.tmem_cols);
+  if (m.resident) {  // one cooperative copy of every layer's W_hi | W_lo for the lifetime of the CTA
+    for (int l = 0; l < m.num_layers; ++l) {
+      const size_t bytes = (size_t)m.k[l] * m.n[l] * 2;
+      const uint4 *gh = reinterpret_cast<const uint4 *>(m.w_hi[l]), *gl = reinterpret_cast<const uint4 *>(m.w_lo[l]);
+      uint4 *sh = reinterpret_cast<uint4 *>(wreg + m.res_off[l]), *sl = reinterpret_cast<uint4 *>(wreg + m.res_off[l] + bytes);
+      for (size_t o = tid; o < bytes / 16; o += THREADS) { sh[o] = __ldg(gh + o); sl[o] = __ldg(gl + o); }
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  uint32_t ring_it = 0;      // number of ring chunks issued so far (all threads count identically)
+  // ---- segments: the first layer is cut into K panels of m.panel channels (one panel unless the built row is too
+  //      wide for shared memory); every later layer is one segment.  seg -> (layer, k_begin, k_len)
+  const int npanels = (m.k[0] + m.panel - 1) / m.panel;
+  const int nsegs = npanels + m.num_layers - 1;
+  auto seg_info = [&](int sg, int &l, int &kb, int &kl) {
+    if (sg < npanels) { l = 0; kb = sg * m.panel; kl = min(m.panel, m.k[0] - kb); }
+    else { l = sg - npanels + 1; kb = 0; kl = m.k[l]; }
+  };
+  // ---- ring bookkeeping (thread 0 only).  The chunk sequence is the same for every tile:
+  //      for segment: for 256-wide block n0: for k0 step kc.  The producer runs ahead across segment AND tile
+  //      boundaries, so the bulk copies of the next layer / next tile overlap epilogues and row building.
+  uint32_t q_prod = 0, q_cons = 0, cpt = 0, total_q = 0;
+  if (!m.resident) {
+    for (int sg = 0; sg < nsegs; ++sg) {
+      int l, kb, kl;
+      seg_info(sg, l, kb, kl);
+      cpt += (uint32_t)(((kl + m.kc - 1) / m.kc) * ((m.n[l] + 255) / 256));
+    }
+    const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    total_q = (uint32_t)my_tiles * cpt;
+  }
+  const uint32_t S = (uint32_t)m.stages;
+  auto produce_one = [&]() {
+    uint32_t c = q_prod % cpt;
+    int l = 0, kb = 0, kl = 0;
+    for (int sg = 0;; ++sg) {
+      seg_info(sg, l, kb, kl);
+      const uint32_t cnt = (uint32_t)(((kl + m.kc - 1) / m.kc) * ((m.n[l] + 255) / 256));
+      if (c < cnt) break;
+      c -= cnt;
+    }
+    const int K = m.k[l], N = m.n[l], kchunks = (kl + m.kc - 1) / m.kc;
+    const int n0 = (int)(c / kchunks) * 256, k0 = kb + (int)(c % kchunks) * m.kc;
+    const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kb + kl - k0);
+    const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
+    if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);      // MMAs of the previous use have retired
+    const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+    const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+    const uint32_t dst = smem_u32(wreg + (size_t)s * 2 * stage_half);
+    mbar_expect_tx(bar_full0 + 8 * s, 2 * bytes);
+    bulk_g2s(dst, gh, bytes, bar_full0 + 8 * s);
+    bulk_g2s(dst + (uint32_t)stage_half, gl, bytes, bar_full0 + 8 * s);
+    ++q_prod;
+  };
+  if (tid == 0 && !m.resident)
+    while (q_prod < total_q && q_prod < S) produce_one();
   uint32_t done_phase = 0;
 
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    build_rows<MODE>(a, aux, a_hi, a_lo, m.k[0] >> 3, tile);
-    fence_proxy_async();
-    __syncthreads();
-
-    for (int l = 0; l < m.num_layers; ++l) {
+    for (int sg = 0; sg < nsegs; ++sg) {
+      int l, kbeg, klen;
+      seg_info(sg, l, kbeg, klen);
       const int K = m.k[l], N = m.n[l];
       const bool last = l == m.num_layers - 1;
-      // ---- MMAs of the layer: N blocks of <= 256 columns, K chunks of m.kc through the ring
-      for (int n0 = 0; n0 < N; n0 += 256) {
-        const int nb = min(256, N - n0);
-        const uint32_t idesc = make_idesc(ROWS, nb);
-        const unsigned char *gw_hi = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2;
-        const unsigned char *gw_lo = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2;
-        for (int k0 = 0; k0 < K; k0 += m.kc) {
-          const int kc = min(m.kc, K - k0);
-          const uint32_t s = ring_it & 1u, use = ring_it >> 1;
-          if (use > 0) mbar_wait(s ? bar_w1 : bar_w0, (use - 1) & 1u);  // MMAs of the previous use have drained
-          unsigned char *st_hi = ring + (size_t)s * 2 * stage_half, *st_lo = st_hi + stage_half;
-          const size_t chunk_bytes = (size_t)(kc >> 3) * nb * 16;
-          const size_t goff = (size_t)(k0 >> 3) * nb * 16;
-          for (size_t o = (size_t)tid * 16; o < chunk_bytes; o += THREADS * 16) {
-            *reinterpret_cast<uint4 *>(st_hi + o) = __ldg(reinterpret_cast<const uint4 *>(gw_hi + goff + o));
-            *reinterpret_cast<uint4 *>(st_lo + o) = __ldg(reinterpret_cast<const uint4 *>(gw_lo + goff + o));
-          }
-          fence_proxy_async();
-          __syncthreads();
-          if (tid == 0) {
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)n0;
-            for (int j = 0; j < kc; j += 16) {
-              const uint32_t ks = (uint32_t)((k0 + j) >> 3);  // first of the two K-slabs of this step
-              const uint64_t ah = make_desc(smem_u32(a_hi + (size_t)ks * SLAB), SLAB, 128);
-              const uint64_t al = make_desc(smem_u32(a_lo + (size_t)ks * SLAB), SLAB, 128);
-              const uint64_t wh = make_desc(smem_u32(st_hi + (size_t)(j >> 3) * nb * 16), (uint32_t)nb * 16, 128);
-              const uint64_t wl = make_desc(smem_u32(st_lo + (size_t)(j >> 3) * nb * 16), (uint32_t)nb * 16, 128);
-              umma_bf16(d_tmem, ah, wh, idesc, (k0 + j) > 0 ? 1u : 0u);
-              umma_bf16(d_tmem, ah, wl, idesc, 1u);
-              umma_bf16(d_tmem, al, wh, idesc, 1u);
-            }
-            umma_commit(s ? bar_w1 : bar_w0);
-          }
-          ++ring_it;
-        }
+      const bool layer_done = sg >= npanels - 1;          // the last panel of layer 0, or any later layer
+      if (l == 0) {
+        build_rows<MODE>(a, aux, a_hi, a_lo, kbeg >> 3, klen >> 3, tile);
+        fence_proxy_async();
+        __syncthreads();
       }
-      if (tid == 0) umma_commit(bar_done);
+      // ---- MMAs of the segment: one thread drives the tensor core (and, in ring mode, the bulk copies)
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo);
+        if (m.resident) {
+          const uint32_t wbase = smem_u32(wreg + m.res_off[l]);
+          for (int n0 = 0; n0 < N; n0 += 256) {
+            const uint32_t nb = (uint32_t)min(256, N - n0);
+            const uint32_t idesc = make_idesc(ROWS, (int)nb);
+            const uint32_t wh = wbase + (uint32_t)n0 * K * 2, wl = wh + (uint32_t)K * N * 2;
+            for (int k0 = kbeg; k0 < kbeg + klen; k0 += 16) {
+              const uint32_t ks = (uint32_t)(k0 >> 3), ka = (uint32_t)((k0 - kbeg) >> 3);
+              issue_kstep(tmem_base + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + ks * nb * 16, wl + ks * nb * 16, nb,
+                          idesc, k0 == 0);
+            }
+          }
+        } else {
+          const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
+          for (int c = 0; c < total; ++c) {
+            const uint32_t q = q_cons, s = q % S;
+            const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+            const uint32_t nb = (uint32_t)min(256, N - n0);
+            const int kc = min(m.kc, kbeg + klen - k0);
+            const uint32_t idesc = make_idesc(ROWS, (int)nb);
+            mbar_wait(bar_full0 + 8 * s, (q / S) & 1u);                            // the chunk has landed
+            tc_fence_after();
+            const uint32_t wh = smem_u32(wreg + (size_t)s * 2 * stage_half), wl = wh + (uint32_t)stage_half;
+            for (int j = 0; j < kc; j += 16) {
+              const uint32_t ka = (uint32_t)((k0 + j - kbeg) >> 3), js = (uint32_t)(j >> 3);
+              issue_kstep(tmem_base + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + js * nb * 16, wl + js * nb * 16, nb,
+                          idesc, k0 + j == 0);
+            }
+            umma_commit(bar_empty0 + 8 * s);                                       // frees the stage when these MMAs retire
+            ++q_cons;
+            // refill a stage whose MMAs were issued at least one chunk ago (its wait will not stall the next issue)
+            if (q_prod < total_q && q_prod - q_cons + 2 <= S) produce_one();
+          }
+        }
+        umma_commit(bar_done);
+        // top up the ring for the next segment / next tile; these waits resolve when the MMAs above retire,
+        // i.e. no later than the done barrier everybody is about to wait on
+        if (!m.resident)
+          while (q_prod < total_q && q_prod - q_cons < S) produce_one();
+      }
+      __syncwarp();
       mbar_wait(bar_done, done_phase);
       done_phase ^= 1u;
       tc_fence_after();
+      if (!layer_done) continue;                          // next K panel of the first layer: rebuild the activation tile
 
       // ---- epilogue: thread = row (TMEM lane 32*(warp&3) + lane); warps 0-3 / 4-7 take alternate 16-column chunks
       const int row = (warp & 3) * 32 + lane;
@@ -448,27 +540,50 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
 }
 
 static size_t smem_bytes(const Chain &m) {
-  const size_t ring = (size_t)4 * (m.kc >> 3) * m.nbmax * 16;
-  return (size_t)(m.kmax >> 3) * SLAB * 2 + (((ring > sizeof(Aux) ? ring : sizeof(Aux)) + 127) & ~(size_t)127) + 64;
+  const size_t a_bytes = (size_t)(m.kmax >> 3) * SLAB * 2;
+  const size_t w = m.resident ? (size_t)m.res_bytes : (size_t)m.stages * 2 * (m.kc >> 3) * m.nbmax * 16;
+  return a_bytes + ((w + 127) & ~(size_t)127) + ((sizeof(Aux) + 127) & ~(size_t)127) + 128;
 }
 
 // fills the derived fields; returns false when the chain does not fit this kernel
 static bool finalize(Chain &m, int mode) {
-  m.kmax = 0;
   m.nbmax = 0;
-  int nmax = 0;
+  int nmax = 0, kmax_rest = 0;
+  size_t wbytes = 0;
   for (int l = 0; l < m.num_layers; ++l) {
-    if (m.k[l] > m.kmax) m.kmax = m.k[l];
+    if (l > 0 && m.k[l] > kmax_rest) kmax_rest = m.k[l];
     const int nb = m.n[l] < 256 ? m.n[l] : 256;
     if (nb > m.nbmax) m.nbmax = nb;
     if (m.n[l] > nmax) nmax = m.n[l];
+    m.res_off[l] = (int)wbytes;
+    wbytes += (size_t)m.k[l] * m.n[l] * 4;   // hi + lo
   }
   if (nmax > 512) return false;
   m.tmem_cols = 32;
   while (m.tmem_cols < nmax) m.tmem_cols <<= 1;
-  if (mode == MODE_FA && m.n[m.num_layers - 1] > m.kmax) return false;  // fp32 staging [128][N] must fit in the A operand (kmax * 512 B)
-  for (m.kc = 32; m.kc >= 16; m.kc >>= 1)
-    if (smem_bytes(m) <= 227 * 1024) return true;
+  m.res_bytes = (int)wbytes;
+  // First-layer K panel: the whole built row when it fits, else 256 / 128 channels per pass.
+  const int panels[3] = {m.k[0], 256, 128};
+  for (int pi = 0; pi < 3; ++pi) {
+    if (pi > 0 && panels[pi] >= m.k[0]) continue;
+    m.panel = panels[pi];
+    m.kmax = m.panel > kmax_rest ? m.panel : kmax_rest;   // capacity of the activation tile
+    if (mode == MODE_FA && m.n[m.num_layers - 1] > m.kmax) continue;  // fp32 staging [128][N] must fit in the A operand (kmax * 512 B)
+    // narrow chains: keep every weight resident if at least two CTAs still fit on an SM
+    m.kc = 32;
+    m.stages = 2;
+    m.resident = 1;
+    if (pi == 0 && smem_bytes(m) <= 113 * 1024) return true;
+    m.resident = 0;
+    // Ring mode: ONE thread drives both the bulk copies and the MMAs, so its per-chunk bookkeeping (two mbarrier
+    // waits, a commit, address arithmetic) must be amortised over as many MMAs as possible: take the largest K chunk
+    // for which two stages fit next to the activation tile; a third stage when it is free.
+    for (m.kc = 256; m.kc >= 16; m.kc >>= 1) {
+      if (m.kc > 16 && m.kc >= 2 * m.kmax) continue;
+      for (m.stages = 3; m.stages >= 2; --m.stages)
+        if (smem_bytes(m) <= 227 * 1024) return true;
+    }
+  }
   return false;
 }
 
