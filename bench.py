@@ -70,14 +70,11 @@ def make_host_batch(seeds, pin):
     return host, chunks
 
 
-def hot_path(model, dev, strict_overlap=True):
-    """One step on device-resident inputs: returns seg_logit (b, 20, np)."""
-    from mvpnet_b200.data import unproject_and_knn
-    rg = unproject_and_knn(dev['depth'], None, dev['pose'], dev['points'], k=KNN, chunk_box=dev['chunk_box'],
-                           cam_inv=dev['cam_inv'])
-    batch = {'images': dev['images'], 'image_xyz': rg['image_xyz'], 'knn_indices': rg['knn_indices'],
-             'points': dev['points_cm']}
-    return model.fast_forward(batch)['seg_logit']
+def hot_path(model, dev, overlap=True):
+    """One step on device-resident inputs (raw depth / pose / images / points): returns seg_logit (b, 20, np)."""
+    batch = {'images': dev['images'], 'points': dev['points_cm'], 'depth': dev['depth'], 'pose': dev['pose'],
+             'cam_inv': dev['cam_inv'], 'chunk_box': dev['chunk_box'], 'k': KNN}
+    return model.fast_forward(batch, overlap=overlap)['seg_logit']
 
 
 class ClockSampler(threading.Thread):
@@ -139,6 +136,42 @@ def algorithmic_bytes_per_chunk():
         out['knn_distance%d' % (i + 1)] = Nd * 12 + Ns * 12 + Nd * 3 * 12
         out['feature_propagation%d' % (i + 1)] = Ns * fp_cs[i] * 4 + Nd * 36 + Nd * fp_cd[i] * 4 + Nd * fp_out[i] * 4
     return out
+
+
+def algorithmic_gflop_per_chunk():
+    """MLP-chain flops per chunk."""
+    return {'feature_aggregation': 0.617, 'set_abstraction1': 0.684, 'set_abstraction2': 0.543, 'set_abstraction3': 0.540,
+            'set_abstraction4': 0.538, 'feature_propagation1': 0.067, 'feature_propagation2': 0.168,
+            'feature_propagation3': 0.470, 'feature_propagation4': 0.805 + 0.310}
+
+
+def stage_bound(name):
+    if name == 'net_2d':
+        return 'cuDNN (out of scope)'
+    if name in ('unproject',):
+        return 'hbm'
+    if name == 'feature_aggregation':
+        return 'hbm (pixel-feature gather) + tensor'
+    if name.startswith('set_abstraction') or name.startswith('feature_propagation'):
+        return 'tensor (tcgen05, bf16 hi/lo x3)'
+    if name.startswith('fps'):
+        return 'serial latency / issue (M-1 dependent arg-max steps, one CTA per cloud)'
+    if name == 'knn_pixels':
+        return 'fp64 CUDA-core compute + latency (exact grid search)'
+    return 'fp32 CUDA-core compute (exhaustive search)'
+
+
+# one launch per stage except the k-NN grid build (bbox, count, scan, scatter, query): kernels of this package per step
+KERNELS_PER_STEP = 1 + 5 + 1 + 4 * 5
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed ncu capture (profiles/r1_ncu_*.md)
+NCU_TRAFFIC_MB = {}
+
+
+def tensor_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path)).get('bf16_tflops', 1590.0))
+    return 1590.0
 
 
 def peaks():
@@ -379,10 +412,7 @@ def main():
     stage_ms = {}
     with torch.no_grad(), engine.profile() as prof:
         for _ in range(max(3, min(args.steps, 5))):
-            from mvpnet_b200.data import unproject_and_knn
-            rg = unproject_and_knn(dev['depth'], None, dev['pose'], dev['points'], k=KNN, chunk_box=dev['chunk_box'], cam_inv=dev['cam_inv'])
-            batch = {'images': dev['images'], 'image_xyz': rg['image_xyz'], 'knn_indices': rg['knn_indices'], 'points': dev['points_cm']}
-            model.fast_forward(batch, overlap=False)
+            hot_path(model, dev, overlap=False)
         for k, v in prof.summary().items():
             stage_ms[k] = float(np.median(v))
 
@@ -397,22 +427,55 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = host_out.numel() * host_out.element_size()
     bytes_pc = algorithmic_bytes_per_chunk()
+    flops_pc = algorithmic_gflop_per_chunk()
     peak, peak_src = peaks()
+    tpeak = tensor_peak()
     mine = {k: v for k, v in stage_ms.items() if k != 'net_2d'}
-    top = max(mine, key=mine.get)
-    achieved = bytes_pc[top] * cpg / (mine[top] / 1e3) / 1e9
-    stages = {k: {'ms': round(v, 4), 'alg_MB': round(bytes_pc.get(k, 0) * cpg / 1e6, 3),
-                  'GBps': round(bytes_pc.get(k, 0) * cpg / (v / 1e3) / 1e9, 1) if k in bytes_pc else None}
-              for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
+    stages = {}
+    for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
+        e = {'ms': round(v, 4), 'bound': stage_bound(k)}
+        if k in bytes_pc:
+            e['alg_MB'] = round(bytes_pc[k] * cpg / 1e6, 3)
+            e['GBps'] = round(bytes_pc[k] * cpg / (v / 1e3) / 1e9, 1)
+            e['hbm_frac'] = round(e['GBps'] / peak, 4)
+        if k in flops_pc:
+            e['alg_GFLOP'] = round(flops_pc[k] * cpg, 2)
+            e['TFLOPs_alg'] = round(flops_pc[k] * cpg / v, 1)                 # fp32-equivalent useful flops
+            e['TFLOPs_issued_bf16'] = round(3 * flops_pc[k] * cpg / v, 1)     # 3 bf16 MMAs per useful MAC (hi/lo split)
+            e['tensor_frac_issued'] = round(3 * flops_pc[k] * cpg / v / tpeak, 4)
+        stages[k] = e
+    # headline roofline: the dominant kernel of this package that is HBM- or tensor-bound by design (the k-NN searches
+    # and FPS are CUDA-core-compute / serial-latency bound: their entries in `stages` carry times and bounds instead)
+    fused = [k for k in mine if k in flops_pc]
+    top = max(fused, key=mine.get)
+    t_fused = sum(mine[k] for k in fused)
+    gf_fused = sum(flops_pc[k] for k in fused) * cpg
+    roof = {'kernel': top, 'bound': 'hbm' if top == 'feature_aggregation' else 'tensor', 'peak_source': peak_src,
+            'ms_per_launch': mine[top], 'traffic': NCU_TRAFFIC_MB.get(top),
+            'traffic_note': 'MB per launch, dram__bytes_read+write from profiles/ (ncu --set full)',
+            'note': 'algorithmic bytes/flops per launch = per-chunk figure (SURVEY 8d) x %d chunks per launch' % cpg}
+    if roof['bound'] == 'hbm':
+        ach = bytes_pc[top] * cpg / (mine[top] / 1e3) / 1e9
+        roof.update({'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak})
+    else:
+        ach = 3 * flops_pc[top] * cpg / mine[top]
+        roof.update({'achieved': ach, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': ach / tpeak,
+                     'note2': 'issued bf16 tensor flops (3 products per useful MAC); useful fp32-equivalent = achieved / 3'})
+    bq_group = mine.get('ball_query1', 0) + mine.get('set_abstraction1', 0)
     line = {'metric': METRIC, 'value': value, 'unit': 'chunks/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'chunks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': ms_e2e / args.steps},
-            'gpu_launches': 23 * args.steps,
-            'roofline': {'kernel': top, 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'ms_per_launch': mine[top],
-                         'note': 'algorithmic bytes per launch = per-chunk bytes (SURVEY 8d) x %d chunks' % cpg},
+            'gpu_launches': KERNELS_PER_STEP * args.steps,
+            'roofline': roof,
+            'fused_mlp_family': {'kernels': len(fused), 'ms_per_step': round(t_fused, 4), 'alg_GFLOP_per_step': round(gf_fused, 1),
+                                 'TFLOPs_alg': round(gf_fused / t_fused, 1), 'TFLOPs_issued_bf16': round(3 * gf_fused / t_fused, 1),
+                                 'tensor_frac_issued': round(3 * gf_fused / t_fused / tpeak, 4), 'peak_TFLOPs_bf16': tpeak},
+            'north_star_targets': {
+                'ball_query+group SA1 (20.93 MB/chunk unfused-algorithmic, fused here)': {
+                    'ms': round(bq_group, 4), 'GBps': round(20.93e6 * cpg / (bq_group / 1e3) / 1e9, 1) if bq_group else None,
+                    'hbm_frac': round(20.93e6 * cpg / (bq_group / 1e3) / 1e9 / peak, 4) if bq_group else None}},
             'stages': stages,
             'hot_path_ms_per_step_excl_net2d': sum(mine.values())}
     if world == 1:

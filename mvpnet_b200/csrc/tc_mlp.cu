@@ -18,6 +18,7 @@
 //   * SA epilogue: one warp reads the 32 TMEM lanes of one centroid (tcgen05.ld 32x32b), so the max over
 //     the K = 32 neighbours is a warp shuffle reduction.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -573,7 +574,7 @@ static bool finalize(Chain &m, int mode) {
     m.kc = 32;
     m.stages = 2;
     m.resident = 1;
-    if (pi == 0 && smem_bytes(m) <= 113 * 1024) return true;
+    if (pi == 0 && smem_bytes(m) <= 160 * 1024) return true;  // <= 113 KB keeps two CTAs per SM; up to 160 KB one CTA without any weight traffic per tile
     m.resident = 0;
     // Ring mode: ONE thread drives both the bulk copies and the MMAs, so its per-chunk bookkeeping (two mbarrier
     // waits, a commit, address arithmetic) must be amortised over as many MMAs as possible: take the largest K chunk
@@ -593,11 +594,20 @@ static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cuda
   const size_t smem = smem_bytes(m);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_fused_mlp: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
-  // persistent: as many CTAs as are resident (registers / shared memory from the occupancy API, TMEM columns here)
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  // persistent: as many CTAs as are resident: shared memory, registers, threads, TMEM columns
+  cudaFuncAttributes fa;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) {
+    const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * THREADS);
+    if (by_regs < per_sm) per_sm = by_regs;
+  }
+  if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
   if (per_sm * m.tmem_cols > 512) per_sm = 512 / m.tmem_cols;
   if (per_sm < 1) per_sm = 1;
+  static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "[tc_fused_mlp mode=%d] tiles=%lld smem=%zu regs=%d per_sm=%d resident=%d kc=%d stages=%d panel=%d kmax=%d tmem=%d\n",
+            MODE, tiles, smem, fa.numRegs, per_sm, m.resident, m.kc, m.stages, m.panel, m.kmax, m.tmem_cols);
   long long grid = (long long)sm_count() * per_sm;
   if (grid > tiles) grid = tiles;
   kern<<<(unsigned)grid, THREADS, smem, stream>>>(a, m, out, tiles);

@@ -315,32 +315,52 @@ class _Streams:
 
 
 def mvpnet3d_forward(model, data_batch, overlap=True):
-    """Fused MVPNet3D.forward (eval): the coordinate-only work of the 3D network runs on a side stream
-    while the 2D network runs; features flow 2D net -> feature_aggregation -> PN2SSG fused chain."""
+    """Fused MVPNet3D.forward (eval).  Everything that depends on coordinates only runs on a side stream
+    while the 2D network runs on the main stream: the data side (depth unprojection + 2D->3D k-NN, when the
+    batch carries `depth`/`pose`/`cam_inv` instead of precomputed `image_xyz`/`knn_indices`) and the geometry of
+    the 3D network (FPS, ball queries, 3-NN).  Features then flow 2D net -> feature_aggregation -> PN2SSG chain.
+
+    data_batch: images (b,nv,3,h,w), points (b,3,np) and EITHER image_xyz (b,nv,h,w,3) + knn_indices (b,np,k)
+    (the reference's DataLoader output, mvpnet_3d.py:88-109) OR depth (b,nv,h,w) + pose (b,nv,4,4) +
+    cam_inv (b,nv,3,3) [+ chunk_box (b,4), k]."""
     images = data_batch['images']
     points = data_batch['points']
     _require_eval_fp32(model, images, points)
     net3d = model.net_3d
-    if not _pn2_supported(net3d) or model.feat_aggreg.mlp is None or not model.feat_aggreg.use_relation \
-            or data_batch['knn_indices'].size(2) > 4:
+    from_depth = 'knn_indices' not in data_batch
+    k = int(data_batch.get('k', 3)) if from_depth else data_batch['knn_indices'].size(2)
+    if not _pn2_supported(net3d) or model.feat_aggreg.mlp is None or not model.feat_aggreg.use_relation or k > 4:
+        if from_depth:
+            data_batch = dict(data_batch)
+            data_batch.update(_data_side(data_batch, points.transpose(1, 2).contiguous(), k))
         return model.forward(data_batch)
     b, nv, _, h, w = images.shape
     main = torch.cuda.current_stream()
     xyz_pm = points.transpose(1, 2).contiguous()
+
+    def coordinate_work():
+        rg = _data_side(data_batch, xyz_pm, k) if from_depth else data_batch
+        return rg, pn2_geometry(net3d, xyz_pm)
+
     if overlap:
         if _Streams.geo is None:
             _Streams.geo = torch.cuda.Stream()
         side = _Streams.geo
         side.wait_stream(main)                     # orders reuse of last call's buffers, keeps overlap
         with torch.cuda.stream(side):
-            geo = pn2_geometry(net3d, xyz_pm)
+            rg, geo = coordinate_work()
     else:
-        geo = pn2_geometry(net3d, xyz_pm)
+        rg, geo = coordinate_work()
     with _stage('net_2d'):
         feat2d = model.net_2d.features(images.reshape(b * nv, *images.shape[2:]))
     feat2d = feat2d.view(b, nv, *feat2d.shape[1:])
-    fa_pm = feature_aggregation(model.feat_aggreg, feat2d, data_batch['image_xyz'], data_batch['knn_indices'],
-                                points, point_major_out=True)
     if overlap:
         main.wait_stream(side)
+    fa_pm = feature_aggregation(model.feat_aggreg, feat2d, rg['image_xyz'], rg['knn_indices'], points, point_major_out=True)
     return {'seg_logit': pn2_features(net3d, geo, fa_pm)}
+
+
+def _data_side(data_batch, xyz_pm, k):
+    from .data import unproject_and_knn
+    return unproject_and_knn(data_batch['depth'], None, data_batch['pose'], xyz_pm, k=k,
+                             chunk_box=data_batch.get('chunk_box'), cam_inv=data_batch['cam_inv'])

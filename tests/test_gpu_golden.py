@@ -116,7 +116,7 @@ def test_pn2_full_config2_forward(fast):
     assert rel_err(logit.cpu().numpy(), g['logit']) < REL_TOL
 
 
-@pytest.mark.parametrize('fast', [False, True])
+@pytest.mark.parametrize('fast', [False, True, 'from_depth'])
 def test_mvpnet_config3(fast):
     from mvpnet_b200.modules import MVPNet3D, PN2SSG
     from mvpnet_b200.unet import UNetResNet34
@@ -132,5 +132,13 @@ def test_mvpnet_config3(fast):
     rg = rgbd_on_gpu(chunk)
     batch = {'images': images, 'image_xyz': rg['image_xyz'], 'knn_indices': rg['knn_indices'],
              'points': torch.from_numpy(chunk['points'].T.copy())[None].cuda()}
-    logit = model.fast_forward(batch)['seg_logit'] if fast else model(batch)['seg_logit']
+    if fast == 'from_depth':      # data side (unproject + 3-NN) inside the fused forward, on the side stream
+        from mvpnet_b200.data import invert_intrinsics
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        raw = {'images': images, 'points': batch['points'], 'depth': t(chunk['depth'])[None], 'pose': t(chunk['pose'])[None],
+               'cam_inv': t(np.broadcast_to(invert_intrinsics(chunk['cam_matrix']), (5, 3, 3)).copy())[None],
+               'chunk_box': t(chunk['chunk_box'])[None], 'k': 3}
+        logit = model.fast_forward(raw)['seg_logit']
+    else:
+        logit = model.fast_forward(batch)['seg_logit'] if fast else model(batch)['seg_logit']
     assert rel_err(logit.cpu().numpy(), g['logit']) < REL_TOL
