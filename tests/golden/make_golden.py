@@ -128,6 +128,21 @@ def main():
                         in_checksum=checksum(pts_s) + checksum(feat_s.numpy()))
     print('pn2_small', logit.shape, float(logit.abs().max()))
 
+    # ---- pn2_small_train: BASELINE config 2 backward — train-mode BatchNorm, loss = sum(logit * w), gradients
+    torch.set_grad_enabled(True)
+    net_t = synthetic.fill_parameters(PN2SSG(16, 20, dropout_prob=0.0, **PN2_SMALL), seed=4).train()
+    feat_t = feat_s.clone().requires_grad_(True)
+    logit_t = net_t({'points': xyz, 'feature': feat_t})['seg_logit']
+    wgt = torch.randn(logit_t.shape, generator=torch.Generator().manual_seed(14))
+    (logit_t * wgt).sum().backward()
+    grads = {n: p_.grad.numpy() for n, p_ in net_t.named_parameters()
+             if n in ('sa_modules.0.mlp.0.conv.weight', 'sa_modules.3.mlp.2.conv.weight', 'fp_modules.0.mlp.0.conv.weight',
+                      'fp_modules.3.mlp.2.bn.weight', 'seg_logit.weight')}
+    np.savez_compressed(os.path.join(HERE, 'pn2_small_train.npz'), logit=logit_t.detach().numpy(), feat_grad=feat_t.grad.numpy(),
+                        **{'g_' + k.replace('.', '_'): v for k, v in grads.items()})
+    print('pn2_small_train', float(logit_t.abs().max()), float(feat_t.grad.abs().max()))
+    torch.set_grad_enabled(False)
+
     # ---- pn2_full: default PN2SSG(64, 20) on an 8192-pt chunk (BASELINE config 2, forward) ---------
     pts_f, _ = synthetic.room_points(8192, seed=0)
     g = torch.Generator().manual_seed(13)
