@@ -341,7 +341,8 @@ def main():
     from mvpnet_b200 import engine
 
     model = build_model(device)
-    model.net_2d.to(memory_format=torch.channels_last)
+    if os.environ.get('MVPNET_B200_UNET_CHANNELS_LAST'):       # strict-fp32 cuDNN is ~1.8x slower in NHWC on B200 (tools/unet_variants.py)
+        model.net_2d.to(memory_format=torch.channels_last)
     cpg = args.chunks_per_gpu
     host, _ = make_host_batch([rank * cpg + i for i in range(cpg)], pin=True)
 

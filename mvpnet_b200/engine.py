@@ -155,6 +155,9 @@ class TcChain:
 # 'tc'  : tcgen05 tensor-core kernels where the chain fits (default), fp32 SIMT kernels elsewhere
 # 'simt': fp32 SIMT kernels everywhere (cross-check / fallback)
 MLP_BACKEND = os.environ.get('MVPNET_B200_MLP', 'tc')
+# copy the 2D feature map to channels-last before the pixel gather (coalesced 256-byte rows) instead of gathering
+# 64 strided channels per pixel straight from the NCHW output of the 2D network
+FA_CHANNELS_LAST_COPY = os.environ.get('MVPNET_B200_FA_CHANNELS_LAST_COPY', '0') == '1'
 _MODE_SA, _MODE_FA, _MODE_FP = 0, 1, 2
 
 
@@ -353,6 +356,9 @@ def mvpnet3d_forward(model, data_batch, overlap=True):
         rg, geo = coordinate_work()
     with _stage('net_2d'):
         feat2d = model.net_2d.features(images.reshape(b * nv, *images.shape[2:]))
+    if FA_CHANNELS_LAST_COPY and feat2d.stride(1) != 1:
+        with _stage('feat2d_to_channels_last'):
+            feat2d = feat2d.contiguous(memory_format=torch.channels_last)   # one pass; pixel rows become 256-byte lines
     feat2d = feat2d.view(b, nv, *feat2d.shape[1:])
     if overlap:
         main.wait_stream(side)
