@@ -130,17 +130,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ---- operand packing ---------------------------------------------------------------------------
+// two fp32 values -> packed bf16 hi pair and packed bf16 lo pair (lo = rn(v - hi)), 5 instructions per pair:
+// one packing convert, two integer ops to re-expand hi, one packed fp32 subtract (FADD2), one packing convert
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t &h, uint32_t &l) {
+  const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+  h = *reinterpret_cast<const uint32_t *>(&hh);
+  uint64_t vv, hf, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v0), "f"(v1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(hf) : "r"(h << 16), "r"(h & 0xffff0000u));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(vv), "l"(hf));
+  float d0, d1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+  const __nv_bfloat162 ll = __floats2bfloat162_rn(d0, d1);
+  l = *reinterpret_cast<const uint32_t *>(&ll);
+}
+
+__device__ __forceinline__ void add_pair(float &a, float &b, float x, float y) {   // packed fp32 add (FADD2), rn like the scalar add
+  uint64_t u, w;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(a), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(x), "f"(y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(u), "l"(w));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(u));
+}
+
 // 8 consecutive channels of one row -> one 16-byte unit of the hi operand and one of the lo operand
 __device__ __forceinline__ void store8(unsigned char *a_hi, unsigned char *a_lo, int row, int kb, const float (&v)[8]) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
+  for (int i = 0; i < 4; ++i) split_pair(v[2 * i], v[2 * i + 1], h[i], l[i]);
   const size_t off = (size_t)kb * SLAB + (size_t)(row >> 3) * 128 + (size_t)(row & 7) * 16;
   *reinterpret_cast<uint4 *>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4 *>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -479,7 +496,8 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 bq = __ldg(bp + q);
-          v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+          add_pair(v[4 * q], v[4 * q + 1], bq.x, bq.y);
+          add_pair(v[4 * q + 2], v[4 * q + 3], bq.z, bq.w);
         }
         if (m.relu[l]) {
 #pragma unroll
@@ -493,16 +511,20 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
           store8(a_hi, a_lo, row, 2 * c + 1, hi8);
         } else if (MODE == MODE_SA) {
           const long long gid = tile * 4 + (warp & 3);
-          float keep = 0.f;
+          // max over the 32 neighbours (= lanes) of 16 columns as a halving butterfly: each exchange keeps half of the
+          // columns, so 8+4+2+1+1 = 16 shuffles instead of 16 x 5; lane L ends up with column L >> 1
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = v[i];
+          for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+            const bool up = (lane & o) != 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
-            if (lane == i) keep = x;
+            for (int i = 0; i < h; ++i) {
+              const float send = up ? v[i] : v[i + h], mine = up ? v[i + h] : v[i];
+              v[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, o));
+            }
           }
-          const int col = c * 16 + lane;
-          if (lane < 16 && col < m.out_channels && gid < a.rows_out) out[gid * m.out_channels + col] = keep;
+          const float keep = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
+          const int col = c * 16 + (lane >> 1);
+          if (!(lane & 1) && col < m.out_channels && gid < a.rows_out) out[gid * m.out_channels + col] = keep;
         } else if (MODE == MODE_FP) {
           const long long pid = tile * ROWS + row;
           if (pid < a.rows_out) {

@@ -317,6 +317,38 @@ class _Streams:
     geo = None
 
 
+FOLD_NET2D_BN = os.environ.get('MVPNET_B200_FOLD_BN', '1') == '1'
+
+
+def _folded_net2d(net):
+    """Inference copy of the 2D UNet with every eval-mode BatchNorm folded into the preceding (transposed)
+    convolution (torch.nn.utils.fusion.fuse_conv_bn_eval): removes ~44 BatchNorm launches (4 ms of the 37 ms
+    2D network at 160 views).  The original module and its state_dict are untouched; anything that is not the
+    UNetResNet34 of this package is returned as is."""
+    from .unet import UNetResNet34
+    if not FOLD_NET2D_BN or not isinstance(net, UNetResNet34):
+        return net
+
+    def build():
+        import copy
+        from torch.nn.utils.fusion import fuse_conv_bn_eval
+        m = copy.deepcopy(net).eval()
+        m.encoder0 = fuse_conv_bn_eval(m.encoder0, m.bn)
+        m.bn = nn.Identity()
+        for layer in (m.encoder1, m.encoder2, m.encoder3, m.encoder4):
+            for blk in layer:
+                blk.conv1, blk.bn1 = fuse_conv_bn_eval(blk.conv1, blk.bn1), nn.Identity()
+                blk.conv2, blk.bn2 = fuse_conv_bn_eval(blk.conv2, blk.bn2), nn.Identity()
+                if blk.downsample is not None:
+                    blk.downsample = nn.Sequential(fuse_conv_bn_eval(blk.downsample[0], blk.downsample[1]))
+        for name in ('deconv4', 'decoder3', 'deconv3', 'decoder2', 'deconv2', 'decoder1', 'deconv1', 'decoder0'):
+            seq = getattr(m, name)
+            fused = fuse_conv_bn_eval(seq[0], seq[1], transpose=isinstance(seq[0], nn.ConvTranspose2d))
+            setattr(m, name, nn.Sequential(fused, seq[2]))
+        return m
+    return _cached(net, 'net2d_folded', build)
+
+
 def mvpnet3d_forward(model, data_batch, overlap=True):
     """Fused MVPNet3D.forward (eval).  Everything that depends on coordinates only runs on a side stream
     while the 2D network runs on the main stream: the data side (depth unprojection + 2D->3D k-NN, when the
@@ -355,7 +387,7 @@ def mvpnet3d_forward(model, data_batch, overlap=True):
     else:
         rg, geo = coordinate_work()
     with _stage('net_2d'):
-        feat2d = model.net_2d.features(images.reshape(b * nv, *images.shape[2:]))
+        feat2d = _folded_net2d(model.net_2d).features(images.reshape(b * nv, *images.shape[2:]))
     if FA_CHANNELS_LAST_COPY and feat2d.stride(1) != 1:
         with _stage('feat2d_to_channels_last'):
             feat2d = feat2d.contiguous(memory_format=torch.channels_last)   # one pass; pixel rows become 256-byte lines
@@ -370,3 +402,33 @@ def _data_side(data_batch, xyz_pm, k):
     from .data import unproject_and_knn
     return unproject_and_knn(data_batch['depth'], None, data_batch['pose'], xyz_pm, k=k,
                              chunk_box=data_batch.get('chunk_box'), cam_inv=data_batch['cam_inv'])
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of the whole forward (static shapes): removes ~800 launches' worth of host work per step
+# ------------------------------------------------------------------------------------------------
+class GraphedForward:
+    """Captures `model.fast_forward(batch)` (both streams, the 2D network included) into one CUDA graph.
+    Call with a batch of the same shapes/dtypes: inputs are copied into the captured static buffers, the graph
+    is replayed and the static output tensor is returned (valid until the next call)."""
+
+    def __init__(self, model, example_batch, warmup=3):
+        self.model = model
+        self.static_in = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in example_batch.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):                      # cuDNN autotune, lazy inits and chain caches happen here
+                model.fast_forward(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = model.fast_forward(self.static_in)['seg_logit']
+
+    def __call__(self, batch):
+        for k, v in batch.items():
+            if torch.is_tensor(v):
+                self.static_in[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
