@@ -62,17 +62,24 @@ int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int64_t M, int 
  * with distance != NULL, ball_query_distance_cuda.ball_query_distance
  * (ball_query_distance.cpp:7-15).  query [B,N1,3], key [B,N2,3] contiguous; index [B,N1,K];
  * distance [B,N1,K] in dtype or NULL.  First K keys in index order with d2 < r*r; tail padded with
- * the first hit (index only, distance pad = -1); no hit -> row of -1. */
+ * the first hit (index only, distance pad = -1); no hit -> row of -1.
+ * workspace: mvp_ball_query_workspace_bytes() bytes (0 -> pass NULL) -> exact uniform-grid search
+ * (device-built, csrc/point_grid.cu) for the clouds it suits; NULL -> exhaustive search.  Identical results. */
+int64_t mvp_ball_query_workspace_bytes(int64_t B, int64_t N1, int64_t N2, float radius, int64_t K, int dtype);
 int mvp_ball_query(const void *query, const void *key, int64_t B, int64_t N1, int64_t N2,
                    float radius, int64_t K, int dtype, int64_t *index, void *distance,
-                   mvp_stream_t stream);
+                   void *workspace, mvp_stream_t stream);
 
 /* ---- 3-NN --------------------------------------------------------------------------------------
  * replaces knn_distance_cuda.knn_distance (knn_distance.cpp:8-16, knn_distance_kernel.cu:154-196)
  * k must be 3 and N2 >= 3.  index [B,N1,3] int64, distance [B,N1,3] squared, ascending, lowest
- * key index first among equal distances. */
+ * key index first among equal distances.
+ * workspace: mvp_knn_distance_workspace_bytes() bytes (0 -> pass NULL) -> exact uniform-grid search
+ * (csrc/point_grid.cu); NULL -> exhaustive search.  Identical results. */
+int64_t mvp_knn_distance_workspace_bytes(int64_t B, int64_t N1, int64_t N2, int dtype);
 int mvp_knn_distance(const void *query, const void *key, int64_t B, int64_t N1, int64_t N2,
-                     int64_t k, int dtype, int64_t *index, void *distance, mvp_stream_t stream);
+                     int64_t k, int dtype, int64_t *index, void *distance, void *workspace,
+                     mvp_stream_t stream);
 
 /* ---- group points ------------------------------------------------------------------------------
  * replaces group_points_cuda.group_points_forward / _backward (group_points.cpp:7-19,

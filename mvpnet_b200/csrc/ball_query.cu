@@ -11,6 +11,7 @@
 // memory (coalesced 128-bit loads when the cloud base is 16-byte aligned; stride-3 AoS reads are
 // bank-conflict free), rows are assembled in shared memory and written as coalesced int64 runs.
 #include "common.cuh"
+#include "point_grid.cu"
 
 namespace mvp {
 
@@ -19,8 +20,10 @@ constexpr int BQ_WARPS = 8;
 template <typename T, bool WITH_DIST, int QPW>
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(const T *__restrict__ query, const T *__restrict__ key, int64_t *__restrict__ index,
-                  T *__restrict__ distance, int N1, int N2, int K, T r2, int tile_keys, int blocks_per_cloud) {
+                  T *__restrict__ distance, int N1, int N2, int K, T r2, int tile_keys, int blocks_per_cloud,
+                  const PgGrid<T> *__restrict__ grids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (grids != nullptr && grids[blockIdx.x / blocks_per_cloud].use) return;   // this cloud is served by the grid kernel
   T *s_key = reinterpret_cast<T *>(smem_raw);                               // [tile_keys*3]
   int *s_row = reinterpret_cast<int *>(s_key + (size_t)tile_keys * 3);      // [warps][QPW][K]
   T *s_dist = reinterpret_cast<T *>(s_row + BQ_WARPS * QPW * K);            // same shape (WITH_DIST)
@@ -98,12 +101,41 @@ ball_query_kernel(const T *__restrict__ query, const T *__restrict__ key, int64_
   }
 }
 
+// the grid path keeps at most K + 64 <= 256 candidate hits per warp in registers while it sorts them
+static inline bool bq_grid_eligible(int64_t B, int64_t N1, int64_t N2, float radius, int64_t K) {
+  return B > 0 && B <= 65535 && K <= 192 && radius > 0.f && radius < 1e30f && pg_worthwhile(N1, N2);
+}
+
 template <typename T>
 static int launch_ball_query(const T *query, const T *key, int64_t B, int64_t N1, int64_t N2, float radius,
-                             int64_t K, int64_t *index, T *distance, cudaStream_t stream) {
+                             int64_t K, int64_t *index, T *distance, void *workspace, cudaStream_t stream) {
   const T r = (T)radius;  // squared in the tensor dtype, ball_query_kernel.cu:73
   const T r2 = r * r;
   const bool wd = distance != nullptr;
+  // ---- exact uniform-grid search (point_grid.cu) for the clouds it suits; the exhaustive kernel below skips them
+  const PgGrid<T> *grids = nullptr;
+  if (workspace != nullptr && bq_grid_eligible(B, N1, N2, radius, K)) {
+    const PgWorkspace<T> w = pg_carve<T>(workspace, B, N2);
+    const T R = r * (T)1.001;
+    if (int rc = pg_build<T>(key, B, N2, R, /*min_cells=*/64, w, stream)) return rc;
+    const int cap = (int)K + 64;
+    const size_t gsm = (size_t)PG_WARPS * (cap + (int)K) * (sizeof(int) + (wd ? sizeof(T) : 0));
+    const int gbpc = (int)((N1 + PG_WARPS - 1) / PG_WARPS);
+    MVP_REQUIRE(B * gbpc < (1LL << 31), MVP_ERR_UNSUPPORTED, "ball_query: too many queries");
+    if (wd) {
+      auto kern = pg_ball_query_kernel<T, true>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+      kern<<<(unsigned)(B * gbpc), PG_WARPS * 32, gsm, stream>>>(query, w.grids, w.cells, w.cell_stride, w.sorted, (int)N1, (int)N2,
+                                                                 (int)K, r2, R, gbpc, index, distance);
+    } else {
+      auto kern = pg_ball_query_kernel<T, false>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm);
+      kern<<<(unsigned)(B * gbpc), PG_WARPS * 32, gsm, stream>>>(query, w.grids, w.cells, w.cell_stride, w.sorted, (int)N1, (int)N2,
+                                                                 (int)K, r2, R, gbpc, index, distance);
+    }
+    if (int rc = launch_status("ball_query (grid)")) return rc;
+    grids = w.grids;
+  }
   // queries per warp: fewer when the grid would not fill the machine
   const int64_t total_q = B * N1;
   int qpw = 4;
@@ -128,7 +160,7 @@ static int launch_ball_query(const T *query, const T *key, int64_t B, int64_t N1
     auto kern = ball_query_kernel<T, WD, Q>;                                                            \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
     kern<<<(unsigned)grid, BQ_WARPS * 32, smem, stream>>>(query, key, index, distance, (int)N1, (int)N2, \
-                                                          (int)K, r2, (int)tile, bpc);                  \
+                                                          (int)K, r2, (int)tile, bpc, grids);           \
   } while (0)
   if (wd) { if (qpw == 4) MVP_BQ(true, 4); else if (qpw == 2) MVP_BQ(true, 2); else MVP_BQ(true, 1); }
   else    { if (qpw == 4) MVP_BQ(false, 4); else if (qpw == 2) MVP_BQ(false, 2); else MVP_BQ(false, 1); }
@@ -138,8 +170,14 @@ static int launch_ball_query(const T *query, const T *key, int64_t B, int64_t N1
 
 }  // namespace mvp
 
+extern "C" int64_t mvp_ball_query_workspace_bytes(int64_t B, int64_t N1, int64_t N2, float radius, int64_t K, int dtype) {
+  using namespace mvp;
+  if (!bq_grid_eligible(B, N1, N2, radius, K)) return 0;
+  return (int64_t)(dtype == MVP_F64 ? pg_workspace_bytes<double>(B, N2) : pg_workspace_bytes<float>(B, N2));
+}
+
 extern "C" int mvp_ball_query(const void *query, const void *key, int64_t B, int64_t N1, int64_t N2, float radius,
-                              int64_t K, int dtype, int64_t *index, void *distance, mvp_stream_t stream) {
+                              int64_t K, int dtype, int64_t *index, void *distance, void *workspace, mvp_stream_t stream) {
   using namespace mvp;
   MVP_REQUIRE(dtype == MVP_F32 || dtype == MVP_F64, MVP_ERR_INVALID_ARG, "ball_query: bad dtype");
   MVP_REQUIRE(K > 0, MVP_ERR_INVALID_ARG, "ball_query: max_neighbors must be > 0");
@@ -149,7 +187,7 @@ extern "C" int mvp_ball_query(const void *query, const void *key, int64_t B, int
   MVP_REQUIRE(query && index && (key || N2 == 0), MVP_ERR_NULL, "ball_query: null pointer");
   if (dtype == MVP_F32)
     return launch_ball_query<float>((const float *)query, (const float *)key, B, N1, N2, radius, K, index,
-                                    (float *)distance, (cudaStream_t)stream);
+                                    (float *)distance, workspace, (cudaStream_t)stream);
   return launch_ball_query<double>((const double *)query, (const double *)key, B, N1, N2, radius, K, index,
-                                   (double *)distance, (cudaStream_t)stream);
+                                   (double *)distance, workspace, (cudaStream_t)stream);
 }

@@ -11,6 +11,7 @@
 // same triple as the reference's single-thread scan.  Keys are staged per CTA in shared memory
 // (128-bit coalesced loads, conflict-free stride-3 reads); outputs are written by lanes 0..2.
 #include "common.cuh"
+#include "point_grid.cu"
 
 namespace mvp {
 
@@ -48,8 +49,9 @@ __device__ __forceinline__ void warp_argmin(double &d, int &idx) {
 template <typename T, int QPW>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn3_kernel(const T *__restrict__ query, const T *__restrict__ key, int64_t *__restrict__ index,
-            T *__restrict__ distance, int N1, int N2, int tile_keys, int blocks_per_cloud) {
+            T *__restrict__ distance, int N1, int N2, int tile_keys, int blocks_per_cloud, const PgGrid<T> *__restrict__ grids) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (grids != nullptr && grids[blockIdx.x / blocks_per_cloud].use) return;   // this cloud is served by the grid kernel
   T *s_key = reinterpret_cast<T *>(smem_raw);
   const int b = blockIdx.x / blocks_per_cloud;
   const int qblock = blockIdx.x % blocks_per_cloud;
@@ -111,9 +113,25 @@ knn3_kernel(const T *__restrict__ query, const T *__restrict__ key, int64_t *__r
   }
 }
 
+static inline bool knn_grid_eligible(int64_t B, int64_t N1, int64_t N2) {
+  return B > 0 && B <= 65535 && pg_worthwhile(N1, N2);
+}
+
 template <typename T>
 static int launch_knn3(const T *query, const T *key, int64_t B, int64_t N1, int64_t N2, int64_t *index,
-                       T *distance, cudaStream_t stream) {
+                       T *distance, void *workspace, cudaStream_t stream) {
+  // ---- exact uniform-grid search (point_grid.cu) for the clouds it suits; the exhaustive kernel below skips them
+  const PgGrid<T> *grids = nullptr;
+  if (workspace != nullptr && knn_grid_eligible(B, N1, N2)) {
+    const PgWorkspace<T> w = pg_carve<T>(workspace, B, N2);
+    if (int rc = pg_build<T>(key, B, N2, (T)0, /*min_cells=*/27, w, stream)) return rc;
+    const int gbpc = (int)((N1 + PG_WARPS - 1) / PG_WARPS);
+    MVP_REQUIRE(B * gbpc < (1LL << 31), MVP_ERR_UNSUPPORTED, "knn_distance: too many queries");
+    pg_knn3_kernel<T><<<(unsigned)(B * gbpc), PG_WARPS * 32, 0, stream>>>(query, w.grids, w.cells, w.cell_stride, w.sorted, (int)N1,
+                                                                          (int)N2, gbpc, index, distance);
+    if (int rc = launch_status("knn_distance (grid)")) return rc;
+    grids = w.grids;
+  }
   const int64_t total_q = B * N1;
   int qpw = 4;
   while (qpw > 1 && (total_q + KNN_WARPS * qpw - 1) / (KNN_WARPS * qpw) < 2 * sm_count()) qpw >>= 1;
@@ -128,7 +146,7 @@ static int launch_knn3(const T *query, const T *key, int64_t B, int64_t N1, int6
     auto kern = knn3_kernel<T, Q>;                                                              \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     kern<<<(unsigned)grid, KNN_WARPS * 32, smem, stream>>>(query, key, index, distance, (int)N1, \
-                                                           (int)N2, (int)tile, bpc);            \
+                                                           (int)N2, (int)tile, bpc, grids);     \
   } while (0)
   if (qpw == 4) MVP_KNN(4); else if (qpw == 2) MVP_KNN(2); else MVP_KNN(1);
 #undef MVP_KNN
@@ -137,8 +155,14 @@ static int launch_knn3(const T *query, const T *key, int64_t B, int64_t N1, int6
 
 }  // namespace mvp
 
+extern "C" int64_t mvp_knn_distance_workspace_bytes(int64_t B, int64_t N1, int64_t N2, int dtype) {
+  using namespace mvp;
+  if (!knn_grid_eligible(B, N1, N2)) return 0;
+  return (int64_t)(dtype == MVP_F64 ? pg_workspace_bytes<double>(B, N2) : pg_workspace_bytes<float>(B, N2));
+}
+
 extern "C" int mvp_knn_distance(const void *query, const void *key, int64_t B, int64_t N1, int64_t N2, int64_t k,
-                                int dtype, int64_t *index, void *distance, mvp_stream_t stream) {
+                                int dtype, int64_t *index, void *distance, void *workspace, mvp_stream_t stream) {
   using namespace mvp;
   MVP_REQUIRE(dtype == MVP_F32 || dtype == MVP_F64, MVP_ERR_INVALID_ARG, "knn_distance: bad dtype");
   MVP_REQUIRE(k == 3, MVP_ERR_INVALID_ARG, "Only support 3-NN.");
@@ -149,7 +173,7 @@ extern "C" int mvp_knn_distance(const void *query, const void *key, int64_t B, i
   MVP_REQUIRE(query && key && index && distance, MVP_ERR_NULL, "knn_distance: null pointer");
   if (dtype == MVP_F32)
     return launch_knn3<float>((const float *)query, (const float *)key, B, N1, N2, index, (float *)distance,
-                              (cudaStream_t)stream);
+                              workspace, (cudaStream_t)stream);
   return launch_knn3<double>((const double *)query, (const double *)key, B, N1, N2, index, (double *)distance,
-                             (cudaStream_t)stream);
+                             workspace, (cudaStream_t)stream);
 }

@@ -11,12 +11,17 @@
 //     the bar is 1e-4) at twice the MMA rate and half the operand bytes of a 3xTF32 scheme.
 //   * operands are K-major, no-swizzle canonical UMMA layout: 8-row x 16-byte core matrices, a K-slab
 //     (8 channels x all rows) is contiguous, so the epilogue of layer l writes layer l+1's A operand with
-//     conflict-free 16-byte stores (one thread = one row = one TMEM lane).
-//   * a layer's MMAs are all issued (one elected thread) before its epilogue runs, so the activation
-//     buffer is rewritten IN PLACE; weights stream through a 2-stage shared-memory ring whose stages are
-//     released by tcgen05.commit -> mbarrier; the host pre-arranges W_hi / W_lo in exactly the ring layout.
+//     conflict-free 16-byte stores (one thread = one row = one TMEM lane), in place.
+//   * warp roles.  A CTA runs NG (1..3) independent TILE GROUPS of 8 worker warps; each group owns an
+//     activation tile in shared memory and a TMEM accumulator and walks its own tiles: build rows -> [MMA] ->
+//     epilogue -> [MMA] -> ... .  One extra warp is the MMA ISSUER (one elected lane serves the groups' requests
+//     round-robin) and one is the WEIGHT PRODUCER (bulk async copies global -> shared-memory ring, running ahead of
+//     the issuer across layers, groups and tiles).  Hand-offs are mbarriers: a_ready[g] (256 worker arrivals ->
+//     issuer), acc_ready[g] (tcgen05.commit -> workers), full/empty per ring stage.  While one group's MMAs run,
+//     the other groups build / run epilogues, so the tensor pipe and the CUDA cores overlap inside one CTA and
+//     the weights (resident for narrow chains, ring otherwise) are shared by the groups.
 //   * SA epilogue: one warp reads the 32 TMEM lanes of one centroid (tcgen05.ld 32x32b), so the max over
-//     the K = 32 neighbours is a warp shuffle reduction.
+//     the K = 32 neighbours is a halving butterfly of warp shuffles.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -26,9 +31,12 @@ namespace mvp {
 namespace tc {
 
 constexpr int ROWS = 128;
-constexpr int THREADS = 256;
+constexpr int GROUP_THREADS = 256;   // 8 worker warps per tile group
+constexpr int MAX_GROUPS = 3;
+constexpr int CTRL_THREADS = 64;     // warp 8*NG: MMA issuer (+ TMEM owner), warp 8*NG+1: weight producer
 constexpr int MAX_LAYERS = 6;
-constexpr int SLAB = ROWS * 16;  // bytes of one K-slab (8 channels) of the A operand
+constexpr int MAX_STAGES = 6;
+constexpr int SLAB = ROWS * 16;      // bytes of one K-slab (8 channels) of the A operand
 
 struct Chain {
   int num_layers;
@@ -40,11 +48,13 @@ struct Chain {
   const float *bias[MAX_LAYERS];          // [n]
   int out_channels;
   int kc;                 // K elements per weight chunk (16 or 32)
-  int kmax;               // max k over layers
+  int kmax;               // max k over layers (capacity of a group's activation tile)
   int nbmax;              // max N-block width over layers (<= 256)
-  int tmem_cols;          // power of two >= max n, >= 32
+  int tmem_cols;          // per group: power of two >= max n, >= 32
+  int tmem_alloc;         // power of two >= groups * tmem_cols
   int resident;           // 1: all weights live in shared memory for the whole kernel (narrow chains)
-  int stages;             // ring depth when not resident (2..4)
+  int stages;             // ring depth when not resident (2..MAX_STAGES)
+  int groups;             // tile groups per CTA (1..MAX_GROUPS)
   int res_off[MAX_LAYERS];  // resident mode: byte offset of layer l's hi block (lo follows at + k*n*2)
   int res_bytes;
   int panel;              // K elements of the first layer built per pass (== k[0] unless the row is too wide for shared memory)
@@ -56,8 +66,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// try_wait suspends in hardware for a bounded time per attempt; a protocol error traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
+  uint32_t ok, spins = 0;
   do {
     asm volatile(
         "{\n"
@@ -68,6 +82,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();
   } while (!ok);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -83,6 +98,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) {   // the 256 workers of tile group g (barrier 0 is __syncthreads)
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GROUP_THREADS) : "memory");
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
@@ -116,17 +134,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// TMEM -> registers, 16 consecutive columns of this warp's 32 lanes.  Issue and wait are separate so that the load
+// of the next chunk is in flight while the current one is processed; the wait names the registers as read-write
+// operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // ---- operand packing ---------------------------------------------------------------------------
@@ -179,7 +203,7 @@ __device__ __forceinline__ void load8(const float *p, bool ok, float (&v)[8]) {
 // so that consecutive lanes write consecutive 16-byte slots of one K-slab (conflict-free); every thread
 // issues the global loads of several units before it converts and stores any of them, which is what hides
 // the gather latency (the two dependent loads index -> row used to be serialised per row).
-struct Aux {                 // per-tile scratch in shared memory
+struct Aux {                 // per-group, per-tile scratch in shared memory
   long long src[ROWS * 3];   // element offset of the source row(s); < 0 = no source (zero row)
   float w[ROWS * 3];         // FP: interpolation weights
   float rel[ROWS * 4];       // SA: xyz - centroid; FA: dx, dy, dz, |d|^2
@@ -192,8 +216,7 @@ __device__ __forceinline__ void zero8(float (&v)[8]) {
 
 template <int MODE>
 __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned char *a_hi, unsigned char *a_lo, int kb_begin,
-                                           int kblocks, long long tile) {
-  const int tid = threadIdx.x;
+                                           int kblocks, long long tile, int tid /* within the group */, int group) {
   // ---------------- phase A (once per tile: the scratch survives the K panels of a wide first layer)
   if (kb_begin == 0 && tid < ROWS) {
     const int r = tid;
@@ -216,8 +239,9 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
       float d[4] = {0.f, 0.f, 0.f, 0.f};
       long long off = -1;
       if (ok) {
-        const int v_ = (int)(j / a.hw), pix = (int)(j - (long long)v_ * a.hw);
-        const int y = pix / a.w, xx = pix - y * a.w;
+        const unsigned ju = (unsigned)j;                       // n_src = nv * h * w < 2^31 (checked by the caller)
+        const unsigned v_ = ju / (unsigned)a.hw, pix = ju - v_ * (unsigned)a.hw;
+        const unsigned y = pix / (unsigned)a.w, xx = pix - y * (unsigned)a.w;
         off = ((long long)b * a.nv + v_) * a.s_n + (long long)y * a.s_h + (long long)xx * a.s_w;
         const float *s = a.xyz + ((size_t)b * a.n_src + j) * 3;
         const float *t = a.new_xyz + pid * 3;
@@ -225,8 +249,7 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
         d[3] = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
       }
       x.src[r] = off;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) x.rel[r * 4 + c] = d[c];
+      *reinterpret_cast<float4 *>(&x.rel[r * 4]) = make_float4(d[0], d[1], d[2], d[3]);
     } else {
       const long long pid = tile * ROWS + r;
       const bool live = pid < a.rows_out;
@@ -248,20 +271,23 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
       for (int k = 0; k < 3; ++k) { x.src[r * 3 + k] = j[k] >= 0 ? b * a.n_src + j[k] : -1; x.w[r * 3 + k] = w[k]; }
     }
   }
-  __syncthreads();
+  group_sync(group);
   // ---------------- phase B: a warp covers 8 rows x 4 K-slabs per step: lane = (slab sub-index << 3) | row sub-index.
   // Loads: 8 rows x 128 contiguous bytes (whole lines); stores: per slab 8 rows x 16 B = 128 contiguous bytes
   // (all 32 banks, conflict-free).
   const int warp = tid >> 5, lane = tid & 31, rs = lane & 7, ks = lane >> 3;
-  const int nblk = 16 * ((kblocks + 3) >> 2);
+  constexpr int NWARP = GROUP_THREADS / 32;
+  // FA: rows 32*k .. 127 carry no pixel (k < 4): 4 row blocks of 8 per live 32-row quarter
+  const int rblocks = MODE == MODE_FA ? 4 * a.k : 16;
+  const int nblk = rblocks * ((kblocks + 3) >> 2);
   if (MODE == MODE_FP) {
     const int Cs = a.feat_channels, Cd = a.skip_channels, sb = Cs >> 3, db = Cd >> 3;
     constexpr int U = 2;
-    for (int wb0 = warp; wb0 < nblk; wb0 += (THREADS / 32) * U) {
+    for (int wb0 = warp; wb0 < nblk; wb0 += NWARP * U) {
       float v0[U][8], v1[U][8], v2[U][8];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        const int wb = wb0 + i * (THREADS / 32);
+        const int wb = wb0 + i * NWARP;
         const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
         zero8(v0[i]); zero8(v1[i]); zero8(v2[i]);
         if (wb < nblk && kl < kblocks) {
@@ -278,7 +304,7 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
       }
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        const int wb = wb0 + i * (THREADS / 32);
+        const int wb = wb0 + i * NWARP;
         const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
         if (wb < nblk && kl < kblocks) {
           if (kb < sb) {
@@ -294,12 +320,13 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
   } else {
     const int cb = a.feat_channels >> 3;
     constexpr int U = 3;
-    for (int wb0 = warp; wb0 < nblk; wb0 += (THREADS / 32) * U) {
+    for (int wb0 = warp; wb0 < nblk; wb0 += NWARP * U) {
       float v[U][8];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        const int wb = wb0 + i * (THREADS / 32);
-        const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
+        const int wb = wb0 + i * NWARP;
+        const int rb = MODE == MODE_FA ? wb % rblocks : (wb & 15), kq = MODE == MODE_FA ? wb / rblocks : (wb >> 4);
+        const int r = rb * 8 + rs, kl = kq * 4 + ks, kb = kb_begin + kl;
         zero8(v[i]);
         if (wb < nblk && kl < kblocks) {
           const long long s0 = x.src[r];
@@ -309,19 +336,21 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
             } else if (a.s_c == 1) {
               load8(a.feat + (s0 < 0 ? 0 : s0) + kb * 8, s0 >= 0, v[i]);
             } else if (s0 >= 0) {
+              const float *p = a.feat + s0 + (long long)(kb * 8) * a.s_c;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) v[i][c] = __ldg(a.feat + s0 + (long long)(kb * 8 + c) * a.s_c);
+              for (int c = 0; c < 8; ++c) v[i][c] = __ldg(p + (long long)c * a.s_c);
             }
           } else if (kb == cb) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) v[i][c] = x.rel[r * 4 + c];
+            const float4 q = *reinterpret_cast<const float4 *>(&x.rel[r * 4]);
+            v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
           }
         }
       }
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        const int wb = wb0 + i * (THREADS / 32);
-        const int r = (wb & 15) * 8 + rs, kl = (wb >> 4) * 4 + ks, kb = kb_begin + kl;
+        const int wb = wb0 + i * NWARP;
+        const int rb = MODE == MODE_FA ? wb % rblocks : (wb & 15), kq = MODE == MODE_FA ? wb / rblocks : (wb >> 4);
+        const int r = rb * 8 + rs, kl = kq * 4 + ks;
         if (wb < nblk && kl < kblocks) store8(a_hi, a_lo, r, kl, v[i]);
       }
     }
@@ -329,8 +358,6 @@ __device__ __forceinline__ void build_rows(const BuildArgs &a, Aux &x, unsigned 
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-constexpr int MAX_STAGES = 4;
-
 __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo, uint32_t nb,
                                             uint32_t idesc, bool first) {
   const uint64_t ah = make_desc(a_hi, SLAB, 128), al = make_desc(a_lo, SLAB, 128);
@@ -340,33 +367,40 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi, uint
   umma_bf16(d_tmem, al, wh, idesc, 1u);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 3)
+// FA staging of the last layer: [pixel slot i][column c][point p], point stride padded to 33 words so that both the
+// row-owner writes (lanes = points) and the reducing reads (lanes = columns) are bank-conflict free
+constexpr int FA_PSTRIDE = 33;
+
+template <int MODE, int NG>
+__global__ void __launch_bounds__(NG *GROUP_THREADS + CTRL_THREADS, 1)
 tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, long long num_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t a_bytes = (size_t)(m.kmax >> 3) * SLAB;
+  constexpr int NW = NG * (GROUP_THREADS / 32);              // worker warps
+  constexpr int NTHREADS = NG * GROUP_THREADS + CTRL_THREADS;
+  const size_t a_bytes = (size_t)(m.kmax >> 3) * SLAB;       // one of {hi, lo} of one group's activation tile
   const size_t stage_half = (size_t)(m.kc >> 3) * m.nbmax * 16;  // one of {hi, lo} of one ring stage
-  unsigned char *a_hi = smem, *a_lo = smem + a_bytes;
-  unsigned char *wreg = smem + 2 * a_bytes;  // resident weights, or the ring [stage][hi|lo]
+  unsigned char *wreg = smem + (size_t)NG * 2 * a_bytes;     // resident weights, or the ring [stage][hi|lo]
   const size_t wreg_bytes = m.resident ? (size_t)m.res_bytes : (size_t)m.stages * 2 * stage_half;
-  Aux &aux = *reinterpret_cast<Aux *>(wreg + ((wreg_bytes + 127) & ~(size_t)127));   // build scratch
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(&aux) + ((sizeof(Aux) + 127) & ~(size_t)127));
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 1);
-  const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + MAX_STAGES), bar_done = smem_u32(bars + 2 * MAX_STAGES);
+  constexpr size_t AUX_BYTES = (sizeof(Aux) + 127) & ~(size_t)127;
+  unsigned char *aux_base = wreg + ((wreg_bytes + 127) & ~(size_t)127);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(aux_base + NG * AUX_BYTES);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2 * MAX_GROUPS);
+  const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + MAX_STAGES);
+  const uint32_t bar_aready0 = smem_u32(bars + 2 * MAX_STAGES), bar_acc0 = smem_u32(bars + 2 * MAX_STAGES + MAX_GROUPS);
 
   if (tid == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_empty0 + 8 * s, 1); }
-    mbar_init(bar_done, 1);
+    for (int g = 0; g < MAX_GROUPS; ++g) { mbar_init(bar_aready0 + 8 * g, GROUP_THREADS); mbar_init(bar_acc0 + 8 * g, 1); }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), (uint32_t)m.tmem_cols);
+  if (warp == NW) tmem_alloc(smem_u32(tmem_slot), (uint32_t)m.tmem_alloc);
   if (m.resident) {  // one cooperative copy of every layer's W_hi | W_lo for the lifetime of the CTA
     for (int l = 0; l < m.num_layers; ++l) {
       const size_t bytes = (size_t)m.k[l] * m.n[l] * 2;
       const uint4 *gh = reinterpret_cast<const uint4 *>(m.w_hi[l]), *gl = reinterpret_cast<const uint4 *>(m.w_lo[l]);
       uint4 *sh = reinterpret_cast<uint4 *>(wreg + m.res_off[l]), *sl = reinterpret_cast<uint4 *>(wreg + m.res_off[l] + bytes);
-      for (size_t o = tid; o < bytes / 16; o += THREADS) { sh[o] = __ldg(gh + o); sl[o] = __ldg(gl + o); }
+      for (size_t o = tid; o < bytes / 16; o += NTHREADS) { sh[o] = __ldg(gh + o); sl[o] = __ldg(gl + o); }
     }
     fence_proxy_async();
   }
@@ -383,193 +417,234 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
     if (sg < npanels) { l = 0; kb = sg * m.panel; kl = min(m.panel, m.k[0] - kb); }
     else { l = sg - npanels + 1; kb = 0; kl = m.k[l]; }
   };
-  // ---- ring bookkeeping (thread 0 only).  The chunk sequence is the same for every tile:
-  //      for segment: for 256-wide block n0: for k0 step kc.  The producer runs ahead across segment AND tile
-  //      boundaries, so the bulk copies of the next layer / next tile overlap epilogues and row building.
-  uint32_t q_prod = 0, q_cons = 0, cpt = 0, total_q = 0;
-  if (!m.resident) {
-    for (int sg = 0; sg < nsegs; ++sg) {
-      int l, kb, kl;
-      seg_info(sg, l, kb, kl);
-      cpt += (uint32_t)(((kl + m.kc - 1) / m.kc) * ((m.n[l] + 255) / 256));
-    }
-    const long long my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    total_q = (uint32_t)my_tiles * cpt;
-  }
+  // tiles of this CTA: blockIdx.x + i * gridDim.x, i in [0, n_my); group g owns i == g (mod NG).  The issuer and the
+  // producer walk the requests in the fixed order  round -> segment -> group.
+  const long long n_my = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const long long rounds = (n_my + NG - 1) / NG;
   const uint32_t S = (uint32_t)m.stages;
-  auto produce_one = [&]() {
-    uint32_t c = q_prod % cpt;
-    int l = 0, kb = 0, kl = 0;
-    for (int sg = 0;; ++sg) {
-      seg_info(sg, l, kb, kl);
-      const uint32_t cnt = (uint32_t)(((kl + m.kc - 1) / m.kc) * ((m.n[l] + 255) / 256));
-      if (c < cnt) break;
-      c -= cnt;
-    }
-    const int K = m.k[l], N = m.n[l], kchunks = (kl + m.kc - 1) / m.kc;
-    const int n0 = (int)(c / kchunks) * 256, k0 = kb + (int)(c % kchunks) * m.kc;
-    const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kb + kl - k0);
-    const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
-    if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);      // MMAs of the previous use have retired
-    const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
-    const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
-    const uint32_t dst = smem_u32(wreg + (size_t)s * 2 * stage_half);
-    mbar_expect_tx(bar_full0 + 8 * s, 2 * bytes);
-    bulk_g2s(dst, gh, bytes, bar_full0 + 8 * s);
-    bulk_g2s(dst + (uint32_t)stage_half, gl, bytes, bar_full0 + 8 * s);
-    ++q_prod;
-  };
-  if (tid == 0 && !m.resident)
-    while (q_prod < total_q && q_prod < S) produce_one();
-  uint32_t done_phase = 0;
 
-  for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    for (int sg = 0; sg < nsegs; ++sg) {
-      int l, kbeg, klen;
-      seg_info(sg, l, kbeg, klen);
-      const int K = m.k[l], N = m.n[l];
-      const bool last = l == m.num_layers - 1;
-      const bool layer_done = sg >= npanels - 1;          // the last panel of layer 0, or any later layer
-      if (l == 0) {
-        build_rows<MODE>(a, aux, a_hi, a_lo, kbeg >> 3, klen >> 3, tile);
+  if (warp < NW) {
+    // =========================== workers: build rows, run the epilogues =============================================
+    const int g = warp / (GROUP_THREADS / 32), ltid = tid - g * GROUP_THREADS, lwarp = ltid >> 5;
+    unsigned char *a_hi = smem + (size_t)g * 2 * a_bytes, *a_lo = a_hi + a_bytes;
+    Aux &aux = *reinterpret_cast<Aux *>(aux_base + g * AUX_BYTES);
+    const uint32_t bar_aready = bar_aready0 + 8 * g, bar_acc = bar_acc0 + 8 * g;
+    const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
+    const int quarter = lwarp & 3, half = lwarp >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t t_lane = t_group + ((uint32_t)(quarter * 32) << 16);
+    const bool live_rows = MODE != MODE_FA || quarter < a.k;     // FA: the rows of quarter >= k carry no pixel
+    uint32_t acc_phase = 0;
+    for (long long i = g; i < n_my; i += NG) {
+      const long long tile = blockIdx.x + i * gridDim.x;
+      for (int sg = 0; sg < nsegs; ++sg) {
+        int l, kbeg, klen;
+        seg_info(sg, l, kbeg, klen);
+        const int N = m.n[l];
+        const bool last = l == m.num_layers - 1;
+        const bool layer_done = sg >= npanels - 1;          // the last panel of layer 0, or any later layer
+        if (l == 0) build_rows<MODE>(a, aux, a_hi, a_lo, kbeg >> 3, klen >> 3, tile, ltid, g);
+        // the activation tile of this segment is complete (built above, or written by the previous epilogue) and
+        // this thread no longer reads the accumulator: hand both to the issuer
         fence_proxy_async();
-        __syncthreads();
-      }
-      // ---- MMAs of the segment: one thread drives the tensor core (and, in ring mode, the bulk copies)
-      if (tid == 0) {
+        tc_fence_before();
+        mbar_arrive(bar_aready);
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1u;
         tc_fence_after();
-        const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo);
-        if (m.resident) {
-          const uint32_t wbase = smem_u32(wreg + m.res_off[l]);
-          for (int n0 = 0; n0 < N; n0 += 256) {
-            const uint32_t nb = (uint32_t)min(256, N - n0);
-            const uint32_t idesc = make_idesc(ROWS, (int)nb);
-            const uint32_t wh = wbase + (uint32_t)n0 * K * 2, wl = wh + (uint32_t)K * N * 2;
-            for (int k0 = kbeg; k0 < kbeg + klen; k0 += 16) {
-              const uint32_t ks = (uint32_t)(k0 >> 3), ka = (uint32_t)((k0 - kbeg) >> 3);
-              issue_kstep(tmem_base + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + ks * nb * 16, wl + ks * nb * 16, nb,
-                          idesc, k0 == 0);
-            }
-          }
-        } else {
-          const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
-          for (int c = 0; c < total; ++c) {
-            const uint32_t q = q_cons, s = q % S;
-            const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
-            const uint32_t nb = (uint32_t)min(256, N - n0);
-            const int kc = min(m.kc, kbeg + klen - k0);
-            const uint32_t idesc = make_idesc(ROWS, (int)nb);
-            mbar_wait(bar_full0 + 8 * s, (q / S) & 1u);                            // the chunk has landed
-            tc_fence_after();
-            const uint32_t wh = smem_u32(wreg + (size_t)s * 2 * stage_half), wl = wh + (uint32_t)stage_half;
-            for (int j = 0; j < kc; j += 16) {
-              const uint32_t ka = (uint32_t)((k0 + j - kbeg) >> 3), js = (uint32_t)(j >> 3);
-              issue_kstep(tmem_base + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + js * nb * 16, wl + js * nb * 16, nb,
-                          idesc, k0 + j == 0);
-            }
-            umma_commit(bar_empty0 + 8 * s);                                       // frees the stage when these MMAs retire
-            ++q_cons;
-            // refill a stage whose MMAs were issued at least one chunk ago (its wait will not stall the next issue)
-            if (q_prod < total_q && q_prod - q_cons + 2 <= S) produce_one();
-          }
-        }
-        umma_commit(bar_done);
-        // top up the ring for the next segment / next tile; these waits resolve when the MMAs above retire,
-        // i.e. no later than the done barrier everybody is about to wait on
-        if (!m.resident)
-          while (q_prod < total_q && q_prod - q_cons < S) produce_one();
-      }
-      __syncwarp();
-      mbar_wait(bar_done, done_phase);
-      done_phase ^= 1u;
-      tc_fence_after();
-      if (!layer_done) continue;                          // next K panel of the first layer: rebuild the activation tile
+        if (!layer_done) continue;                          // next K panel of the first layer: rebuild the activation tile
 
-      // ---- epilogue: thread = row (TMEM lane 32*(warp&3) + lane); warps 0-3 / 4-7 take alternate 16-column chunks
-      const int row = (warp & 3) * 32 + lane;
-      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      float *fbuf = reinterpret_cast<float *>(smem);  // MODE_FA last layer: [ROWS][N] fp32 staging over the (dead) A operand
-      for (int c = (warp >> 2); c * 16 < N; c += 2) {
-        float v[16];
-        tmem_ld16(t_lane + (uint32_t)(c * 16), v);
-        const float4 *bp = reinterpret_cast<const float4 *>(m.bias[l] + c * 16);
+        // ---- epilogue: thread = row (TMEM lane 32 * quarter + lane); the two warps of a quarter take alternate
+        //      16-column chunks; the TMEM load of the next chunk is in flight while this one is processed
+        float *fbuf = reinterpret_cast<float *>(a_hi);      // MODE_FA last layer: fp32 staging over the (dead) A operand
+        if (live_rows) {
+          uint32_t rn[16];
+          int c = half;
+          if (c * 16 < N) tmem_ld16_issue(t_lane + (uint32_t)(c * 16), rn);
+          while (c * 16 < N) {
+            float v[16];
+            tmem_ld_wait(rn);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 bq = __ldg(bp + q);
-          add_pair(v[4 * q], v[4 * q + 1], bq.x, bq.y);
-          add_pair(v[4 * q + 2], v[4 * q + 3], bq.z, bq.w);
-        }
-        if (m.relu[l]) {
+            for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
+            if ((c + 2) * 16 < N) tmem_ld16_issue(t_lane + (uint32_t)((c + 2) * 16), rn);
+            const float4 *bp = reinterpret_cast<const float4 *>(m.bias[l] + c * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (!last) {
-          float lo8[8], hi8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { lo8[i] = v[i]; hi8[i] = v[8 + i]; }
-          store8(a_hi, a_lo, row, 2 * c, lo8);
-          store8(a_hi, a_lo, row, 2 * c + 1, hi8);
-        } else if (MODE == MODE_SA) {
-          const long long gid = tile * 4 + (warp & 3);
-          // max over the 32 neighbours (= lanes) of 16 columns as a halving butterfly: each exchange keeps half of the
-          // columns, so 8+4+2+1+1 = 16 shuffles instead of 16 x 5; lane L ends up with column L >> 1
-#pragma unroll
-          for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < h; ++i) {
-              const float send = up ? v[i] : v[i + h], mine = up ? v[i + h] : v[i];
-              v[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, o));
+            for (int q = 0; q < 4; ++q) {
+              const float4 bq = __ldg(bp + q);
+              add_pair(v[4 * q], v[4 * q + 1], bq.x, bq.y);
+              add_pair(v[4 * q + 2], v[4 * q + 3], bq.z, bq.w);
             }
-          }
-          const float keep = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
-          const int col = c * 16 + (lane >> 1);
-          if (!(lane & 1) && col < m.out_channels && gid < a.rows_out) out[gid * m.out_channels + col] = keep;
-        } else if (MODE == MODE_FP) {
-          const long long pid = tile * ROWS + row;
-          if (pid < a.rows_out) {
+            if (m.relu[l]) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c * 16 + i < m.out_channels) out[pid * m.out_channels + c * 16 + i] = v[i];
-          }
-        } else {
+              for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+            }
+            if (!last) {
+              float lo8[8], hi8[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) fbuf[(size_t)row * N + c * 16 + i] = v[i];
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async();
-      __syncthreads();
-      tc_fence_after();
-      if (last && MODE == MODE_FA) {
-        for (int e = tid; e < 32 * m.out_channels; e += THREADS) {
-          const int p = e / m.out_channels, c = e - p * m.out_channels;
-          const long long pid = tile * 32 + p;
-          if (pid >= a.rows_out) continue;
-          float v = fbuf[(size_t)p * N + c];
-          for (int i = 1; i < a.k; ++i) {
-            const float u = fbuf[(size_t)(i * 32 + p) * N + c];
-            v = a.reduce == REDUCE_SUM ? __fadd_rn(v, u) : fmaxf(v, u);
+              for (int q = 0; q < 8; ++q) { lo8[q] = v[q]; hi8[q] = v[8 + q]; }
+              store8(a_hi, a_lo, row, 2 * c, lo8);
+              store8(a_hi, a_lo, row, 2 * c + 1, hi8);
+            } else if (MODE == MODE_SA) {
+              const long long gid = tile * 4 + quarter;
+              // max over the 32 neighbours (= lanes) of 16 columns as a halving butterfly: each exchange keeps half of
+              // the columns, so 8+4+2+1+1 = 16 shuffles instead of 16 x 5; lane L ends up with column L >> 1
+#pragma unroll
+              for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int q = 0; q < h; ++q) {
+                  const float send = up ? v[q] : v[q + h], mine = up ? v[q + h] : v[q];
+                  v[q] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, o));
+                }
+              }
+              const float keep = fmaxf(v[0], __shfl_xor_sync(0xffffffffu, v[0], 1));
+              const int col = c * 16 + (lane >> 1);
+              if (!(lane & 1) && col < m.out_channels && gid < a.rows_out) out[gid * m.out_channels + col] = keep;
+            } else if (MODE == MODE_FP) {
+              const long long pid = tile * ROWS + row;
+              if (pid < a.rows_out) {
+                float *op = out + pid * m.out_channels + c * 16;
+                if ((m.out_channels & 3) == 0) {             // rows are 16-byte aligned: 128-bit stores
+#pragma unroll
+                  for (int q = 0; q < 4; ++q)
+                    if (c * 16 + 4 * q < m.out_channels)
+                      *reinterpret_cast<float4 *>(op + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                } else {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q)
+                    if (c * 16 + q < m.out_channels) op[q] = v[q];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) fbuf[(size_t)(quarter * N + c * 16 + q) * FA_PSTRIDE + lane] = v[q];
+            }
+            c += 2;
           }
-          out[pid * m.out_channels + c] = v;
         }
-        __syncthreads();
+        if (last && MODE == MODE_FA) {
+          group_sync(g);
+          // reduce over the k pixel slots; consecutive threads take consecutive channels (coalesced rows of `out`)
+          const int oc = m.out_channels;
+          int p = ltid / oc, c = ltid - p * oc;
+          const int dp = GROUP_THREADS / oc, dc = GROUP_THREADS - dp * oc;
+          for (; p < 32; p += dp, c += dc) {
+            if (c >= oc) { c -= oc; ++p; if (p >= 32) break; }
+            const long long pid = tile * 32 + p;
+            if (pid >= a.rows_out) continue;
+            float v = fbuf[(size_t)c * FA_PSTRIDE + p];
+            for (int q = 1; q < a.k; ++q) {
+              const float u = fbuf[(size_t)(q * N + c) * FA_PSTRIDE + p];
+              v = a.reduce == REDUCE_SUM ? __fadd_rn(v, u) : fmaxf(v, u);
+            }
+            out[pid * oc + c] = v;
+          }
+          group_sync(g);                                      // the staging area is the next tile's A operand
+        }
       }
     }
+  } else if (warp == NW) {
+    // =========================== MMA issuer (one elected lane) ======================================================
+    if (lane == 0) {
+      uint32_t ph[MAX_GROUPS] = {0u, 0u, 0u};
+      uint32_t q_cons = 0;
+      for (long long r = 0; r < rounds; ++r) {
+        for (int sg = 0; sg < nsegs; ++sg) {
+          int l, kbeg, klen;
+          seg_info(sg, l, kbeg, klen);
+          const int K = m.k[l], N = m.n[l];
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (r * NG + g >= n_my) continue;
+            mbar_wait(bar_aready0 + 8 * g, ph[g]);
+            ph[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t a_hi_s = smem_u32(smem + (size_t)g * 2 * a_bytes), a_lo_s = a_hi_s + (uint32_t)a_bytes;
+            const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
+            if (m.resident) {
+              const uint32_t wbase = smem_u32(wreg + m.res_off[l]);
+              for (int n0 = 0; n0 < N; n0 += 256) {
+                const uint32_t nb = (uint32_t)min(256, N - n0);
+                const uint32_t idesc = make_idesc(ROWS, (int)nb);
+                const uint32_t wh = wbase + (uint32_t)n0 * K * 2, wl = wh + (uint32_t)K * N * 2;
+                for (int k0 = kbeg; k0 < kbeg + klen; k0 += 16) {
+                  const uint32_t ks = (uint32_t)(k0 >> 3), ka = (uint32_t)((k0 - kbeg) >> 3);
+                  issue_kstep(t_group + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + ks * nb * 16, wl + ks * nb * 16, nb,
+                              idesc, k0 == 0);
+                }
+              }
+            } else {
+              const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
+              for (int c = 0; c < total; ++c) {
+                const uint32_t s = q_cons % S;
+                const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+                const uint32_t nb = (uint32_t)min(256, N - n0);
+                const int kc = min(m.kc, kbeg + klen - k0);
+                const uint32_t idesc = make_idesc(ROWS, (int)nb);
+                mbar_wait(bar_full0 + 8 * s, (q_cons / S) & 1u);                       // the chunk has landed
+                tc_fence_after();
+                const uint32_t wh = smem_u32(wreg + (size_t)s * 2 * stage_half), wl = wh + (uint32_t)stage_half;
+                for (int j = 0; j < kc; j += 16) {
+                  const uint32_t ka = (uint32_t)((k0 + j - kbeg) >> 3), js = (uint32_t)(j >> 3);
+                  issue_kstep(t_group + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + js * nb * 16, wl + js * nb * 16, nb,
+                              idesc, k0 + j == 0);
+                }
+                umma_commit(bar_empty0 + 8 * s);                                       // frees the stage when these MMAs retire
+                ++q_cons;
+              }
+            }
+            umma_commit(bar_acc0 + 8 * g);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (!m.resident) {
+    // =========================== weight producer (one elected lane): same request order, runs ahead =================
+    if (lane == 0) {
+      uint32_t q_prod = 0;
+      for (long long r = 0; r < rounds; ++r) {
+        for (int sg = 0; sg < nsegs; ++sg) {
+          int l, kbeg, klen;
+          seg_info(sg, l, kbeg, klen);
+          const int K = m.k[l], N = m.n[l];
+          const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
+          for (int g = 0; g < NG; ++g) {
+            if (r * NG + g >= n_my) continue;
+            for (int c = 0; c < total; ++c) {
+              const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+              const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kbeg + klen - k0);
+              const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
+              if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);  // MMAs of the previous use have retired
+              const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+              const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+              const uint32_t dst = smem_u32(wreg + (size_t)s * 2 * stage_half);
+              mbar_expect_tx(bar_full0 + 8 * s, 2 * bytes);
+              bulk_g2s(dst, gh, bytes, bar_full0 + 8 * s);
+              bulk_g2s(dst + (uint32_t)stage_half, gl, bytes, bar_full0 + 8 * s);
+              ++q_prod;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)m.tmem_cols);
+  if (warp == NW) tmem_dealloc(tmem_base, (uint32_t)m.tmem_alloc);
 }
 
 static size_t smem_bytes(const Chain &m) {
-  const size_t a_bytes = (size_t)(m.kmax >> 3) * SLAB * 2;
+  const size_t a_bytes = (size_t)m.groups * (m.kmax >> 3) * SLAB * 2;
   const size_t w = m.resident ? (size_t)m.res_bytes : (size_t)m.stages * 2 * (m.kc >> 3) * m.nbmax * 16;
-  return a_bytes + ((w + 127) & ~(size_t)127) + ((sizeof(Aux) + 127) & ~(size_t)127) + 128;
+  return a_bytes + ((w + 127) & ~(size_t)127) + m.groups * ((sizeof(Aux) + 127) & ~(size_t)127) + 256;
 }
 
+constexpr size_t SMEM_CAP = 227 * 1024;
+
 // fills the derived fields; returns false when the chain does not fit this kernel
-static bool finalize(Chain &m, int mode) {
+static bool finalize(Chain &m, int mode, int fa_k) {
   m.nbmax = 0;
   int nmax = 0, kmax_rest = 0;
   size_t wbytes = 0;
@@ -591,49 +666,82 @@ static bool finalize(Chain &m, int mode) {
     if (pi > 0 && panels[pi] >= m.k[0]) continue;
     m.panel = panels[pi];
     m.kmax = m.panel > kmax_rest ? m.panel : kmax_rest;   // capacity of the activation tile
-    if (mode == MODE_FA && m.n[m.num_layers - 1] > m.kmax) continue;  // fp32 staging [128][N] must fit in the A operand (kmax * 512 B)
-    // narrow chains: keep every weight resident if at least two CTAs still fit on an SM
-    m.kc = 32;
-    m.stages = 2;
-    m.resident = 1;
-    if (pi == 0 && smem_bytes(m) <= 160 * 1024) return true;  // <= 113 KB keeps two CTAs per SM; up to 160 KB one CTA without any weight traffic per tile
-    m.resident = 0;
-    // Ring mode: ONE thread drives both the bulk copies and the MMAs, so its per-chunk bookkeeping (two mbarrier
-    // waits, a commit, address arithmetic) must be amortised over as many MMAs as possible: take the largest K chunk
-    // for which two stages fit next to the activation tile; a third stage when it is free.
-    for (m.kc = 256; m.kc >= 16; m.kc >>= 1) {
-      if (m.kc > 16 && m.kc >= 2 * m.kmax) continue;
-      for (m.stages = 3; m.stages >= 2; --m.stages)
-        if (smem_bytes(m) <= 227 * 1024) return true;
+    // FA: the fp32 staging [k][N][33] of the last layer must fit in the group's (dead) A operand (kmax * 512 B)
+    if (mode == MODE_FA && (size_t)fa_k * m.n[m.num_layers - 1] * FA_PSTRIDE * 4 > (size_t)m.kmax * 512) continue;
+    // Most tile groups first (they overlap MMAs with builds / epilogues inside the CTA and share the weights);
+    // per group count: resident weights if they fit, else the deepest ring of 32- or 16-channel chunks.
+    for (m.groups = MAX_GROUPS; m.groups >= 1; --m.groups) {
+      if (m.groups * m.tmem_cols > 512) continue;
+      m.tmem_alloc = 32;
+      while (m.tmem_alloc < m.groups * m.tmem_cols) m.tmem_alloc <<= 1;
+      m.kc = 32; m.stages = 2; m.resident = 1;
+      if (pi == 0 && smem_bytes(m) <= SMEM_CAP) return true;
+      m.resident = 0;
+      int best_kc = 0, best_stages = 0;
+      for (int kc = 32; kc >= 16; kc >>= 1) {
+        m.kc = kc;
+        for (m.stages = MAX_STAGES; m.stages >= 2; --m.stages)
+          if (smem_bytes(m) <= SMEM_CAP) break;
+        if (m.stages >= 2 && m.stages * kc > best_stages * best_kc) { best_kc = kc; best_stages = m.stages; }
+      }
+      // a ring shallower than 64 channels in flight starves the issuer: try fewer groups first
+      if (best_kc && (best_stages * best_kc >= 64 || m.groups == 1)) { m.kc = best_kc; m.stages = best_stages; return true; }
     }
   }
   return false;
 }
 
-template <int MODE>
-static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cudaStream_t stream) {
-  auto kern = tc_fused_mlp_kernel<MODE>;
+template <int MODE, int NG>
+static int launch_ng(const BuildArgs &a, const Chain &m, float *out, long long tiles, cudaStream_t stream) {
+  auto kern = tc_fused_mlp_kernel<MODE, NG>;
   const size_t smem = smem_bytes(m);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_fused_mlp: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   // persistent: as many CTAs as are resident: shared memory, registers, threads, TMEM columns
+  constexpr int THREADS = NG * GROUP_THREADS + CTRL_THREADS;
   cudaFuncAttributes fa;
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  int per_sm = (int)(SMEM_CAP / (smem + 1024));
   if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) {
     const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * THREADS);
     if (by_regs < per_sm) per_sm = by_regs;
   }
   if (per_sm > 2048 / THREADS) per_sm = 2048 / THREADS;
-  if (per_sm * m.tmem_cols > 512) per_sm = 512 / m.tmem_cols;
+  if (per_sm * m.tmem_alloc > 512) per_sm = 512 / m.tmem_alloc;
   if (per_sm < 1) per_sm = 1;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
   if (debug)
-    fprintf(stderr, "[tc_fused_mlp mode=%d] tiles=%lld smem=%zu regs=%d per_sm=%d resident=%d kc=%d stages=%d panel=%d kmax=%d tmem=%d\n",
-            MODE, tiles, smem, fa.numRegs, per_sm, m.resident, m.kc, m.stages, m.panel, m.kmax, m.tmem_cols);
+    fprintf(stderr, "[tc_fused_mlp mode=%d] tiles=%lld groups=%d smem=%zu regs=%d per_sm=%d resident=%d kc=%d stages=%d panel=%d kmax=%d tmem=%d/%d\n",
+            MODE, tiles, NG, smem, fa.numRegs, per_sm, m.resident, m.kc, m.stages, m.panel, m.kmax, m.tmem_cols, m.tmem_alloc);
   long long grid = (long long)sm_count() * per_sm;
-  if (grid > tiles) grid = tiles;
+  const long long want = (tiles + NG - 1) / NG;
+  if (grid > want) grid = want;
   kern<<<(unsigned)grid, THREADS, smem, stream>>>(a, m, out, tiles);
   return launch_status("tc_fused_mlp");
+}
+
+template <int MODE>
+static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cudaStream_t stream) {
+  // fewer groups when there are not enough tiles to give every SM NG of them: spread over the SMs first
+  int ng = m.groups;
+  const long long per_sm_tiles = tiles / sm_count();
+  if (per_sm_tiles < ng) ng = per_sm_tiles < 1 ? 1 : (int)per_sm_tiles;
+  static const char *force = getenv("MVPNET_B200_TC_GROUPS");
+  if (force && atoi(force) >= 1 && atoi(force) < ng) ng = atoi(force);
+  if (ng != m.groups) {
+    m.groups = ng;
+    m.tmem_alloc = 32;
+    while (m.tmem_alloc < m.groups * m.tmem_cols) m.tmem_alloc <<= 1;
+    if (!m.resident) {                         // the freed activation tiles deepen the ring
+      for (int s = MAX_STAGES; s > m.stages; --s) {
+        Chain t = m;
+        t.stages = s;
+        if (smem_bytes(t) <= SMEM_CAP) { m.stages = s; break; }
+      }
+    }
+  }
+  if (ng == 3) return launch_ng<MODE, 3>(a, m, out, tiles, stream);
+  if (ng == 2) return launch_ng<MODE, 2>(a, m, out, tiles, stream);
+  return launch_ng<MODE, 1>(a, m, out, tiles, stream);
 }
 
 }  // namespace tc
@@ -642,7 +750,7 @@ static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cuda
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-static int mvp_tc_to_chain(const mvp_tc_chain_t *c, int k0_min, int mode, mvp::tc::Chain *m) {
+static int mvp_tc_to_chain(const mvp_tc_chain_t *c, int k0_min, int mode, int fa_k, mvp::tc::Chain *m) {
   using namespace mvp;
   MVP_REQUIRE(c, MVP_ERR_NULL, "tc_fused_mlp: null chain");
   MVP_REQUIRE(c->num_layers >= 1 && c->num_layers <= tc::MAX_LAYERS, MVP_ERR_INVALID_ARG, "tc_fused_mlp: 1..6 layers");
@@ -660,7 +768,7 @@ static int mvp_tc_to_chain(const mvp_tc_chain_t *c, int k0_min, int mode, mvp::t
     m->w_hi[l] = (const __nv_bfloat16 *)c->w_hi[l]; m->w_lo[l] = (const __nv_bfloat16 *)c->w_lo[l]; m->bias[l] = c->bias[l];
   }
   MVP_REQUIRE(c->out_channels > 0 && c->out_channels <= c->n[c->num_layers - 1], MVP_ERR_INVALID_ARG, "tc_fused_mlp: bad out_channels");
-  MVP_REQUIRE(tc::finalize(*m, mode), MVP_ERR_UNSUPPORTED, "tc_fused_mlp: chain too wide for shared memory / TMEM (kmax=%d)", m->kmax);
+  MVP_REQUIRE(tc::finalize(*m, mode, fa_k), MVP_ERR_UNSUPPORTED, "tc_fused_mlp: chain too wide for shared memory / TMEM (kmax=%d)", m->kmax);
   return 0;
 }
 
@@ -669,7 +777,7 @@ extern "C" int mvp_tc_chain_supported(const mvp_tc_chain_t *c, int mode) {
   if (!c || c->num_layers < 1 || c->num_layers > mvp::tc::MAX_LAYERS) return 0;
   m.num_layers = c->num_layers;
   for (int l = 0; l < c->num_layers; ++l) { m.k[l] = c->k[l]; m.n[l] = c->n[l]; }
-  return mvp::tc::finalize(m, mode) ? 1 : 0;
+  return mvp::tc::finalize(m, mode, 4) ? 1 : 0;
 }
 
 extern "C" int mvp_tc_fused_set_abstraction(const float *feat, int64_t C, const float *xyz, const float *new_xyz,
@@ -680,7 +788,7 @@ extern "C" int mvp_tc_fused_set_abstraction(const float *feat, int64_t C, const 
   MVP_REQUIRE(C % 8 == 0 && C >= 0, MVP_ERR_UNSUPPORTED, "tc_fused_set_abstraction: feature channels must be a multiple of 8");
   MVP_REQUIRE(B >= 0 && N > 0 && M >= 0, MVP_ERR_INVALID_ARG, "tc_fused_set_abstraction: bad sizes");
   tc::Chain m;
-  if (int rc = mvp_tc_to_chain(chain, (int)C + 3, MODE_SA, &m)) return rc;
+  if (int rc = mvp_tc_to_chain(chain, (int)C + 3, MODE_SA, 0, &m)) return rc;
   if (B * M == 0) return 0;
   MVP_REQUIRE(xyz && new_xyz && nbr && out && (feat || C == 0), MVP_ERR_NULL, "tc_fused_set_abstraction: null pointer");
   MVP_REQUIRE(((uintptr_t)feat & 15) == 0, MVP_ERR_INVALID_ARG, "tc_fused_set_abstraction: feat must be 16-byte aligned");
@@ -698,8 +806,9 @@ extern "C" int mvp_tc_fused_feature_aggregation(const float *feat2d, int64_t s_n
   MVP_REQUIRE(K >= 1 && K <= 4, MVP_ERR_UNSUPPORTED, "tc_fused_feature_aggregation: k must be in [1, 4]");
   MVP_REQUIRE(C % 8 == 0 && C > 0, MVP_ERR_UNSUPPORTED, "tc_fused_feature_aggregation: feature channels must be a multiple of 8");
   MVP_REQUIRE(B >= 0 && Np >= 0 && nv > 0 && h > 0 && w > 0, MVP_ERR_INVALID_ARG, "tc_fused_feature_aggregation: bad sizes");
+  MVP_REQUIRE(nv * h * w < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_fused_feature_aggregation: more than 2^31 pixels per cloud");
   tc::Chain m;
-  if (int rc = mvp_tc_to_chain(chain, (int)C + 4, MODE_FA, &m)) return rc;
+  if (int rc = mvp_tc_to_chain(chain, (int)C + 4, MODE_FA, (int)K, &m)) return rc;
   if (B * Np == 0) return 0;
   MVP_REQUIRE(feat2d && pix_xyz && points && knn && out, MVP_ERR_NULL, "tc_fused_feature_aggregation: null pointer");
   if (s_c == 1)
@@ -720,7 +829,7 @@ extern "C" int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_
               "tc_fused_feature_propagation: channel counts must be multiples of 8");
   MVP_REQUIRE(B >= 0 && Ns > 0 && Nd >= 0, MVP_ERR_INVALID_ARG, "tc_fused_feature_propagation: bad sizes");
   tc::Chain m;
-  if (int rc = mvp_tc_to_chain(chain, (int)(Cs + Cd), MODE_FP, &m)) return rc;
+  if (int rc = mvp_tc_to_chain(chain, (int)(Cs + Cd), MODE_FP, 0, &m)) return rc;
   if (B * Nd == 0) return 0;
   MVP_REQUIRE(sparse_feat && idx && dist2 && out && (skip || Cd == 0), MVP_ERR_NULL, "tc_fused_feature_propagation: null pointer");
   MVP_REQUIRE((((uintptr_t)sparse_feat | (uintptr_t)skip) & 15) == 0, MVP_ERR_INVALID_ARG,

@@ -10,6 +10,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/mvpnet_b200.h"
@@ -63,6 +64,13 @@ void check_query_key(const at::Tensor &query, const at::Tensor &key) {
   TORCH_CHECK(query.device() == key.device(), "query and key must be on the same device");
 }
 
+// workspace of the exact uniform-grid searches (csrc/point_grid.cu); MVPNET_B200_GRID=0 forces the exhaustive kernels
+at::Tensor grid_workspace(const at::Tensor &like, int64_t bytes) {
+  static const bool enabled = [] { const char *e = getenv("MVPNET_B200_GRID"); return !(e && e[0] == '0'); }();
+  if (!enabled || bytes <= 0) return at::Tensor();
+  return at::empty({bytes}, like.options().dtype(at::kByte));
+}
+
 // ball_query.cpp:7-15
 at::Tensor ball_query(const at::Tensor query, const at::Tensor key, const float radius, const int64_t max_neighbors) {
   check_query_key(query, key);
@@ -70,8 +78,10 @@ at::Tensor ball_query(const at::Tensor query, const at::Tensor key, const float 
   const int dt = dtype_of(query, "query");
   c10::cuda::CUDAGuard guard(query.device());
   auto index = at::empty({query.size(0), query.size(1), max_neighbors}, query.options().dtype(at::kLong));
+  at::Tensor work = grid_workspace(query, mvp_ball_query_workspace_bytes(query.size(0), query.size(1), key.size(1), radius, max_neighbors, dt));
   check_rc(mvp_ball_query(query.data_ptr(), key.data_ptr(), query.size(0), query.size(1), key.size(1), radius,
-                          max_neighbors, dt, index.data_ptr<int64_t>(), nullptr, cur_stream()));
+                          max_neighbors, dt, index.data_ptr<int64_t>(), nullptr, work.defined() ? work.data_ptr() : nullptr,
+                          cur_stream()));
   return index;
 }
 
@@ -84,8 +94,10 @@ std::vector<at::Tensor> ball_query_distance(const at::Tensor query, const at::Te
   c10::cuda::CUDAGuard guard(query.device());
   auto index = at::empty({query.size(0), query.size(1), max_neighbors}, query.options().dtype(at::kLong));
   auto distance = at::empty({query.size(0), query.size(1), max_neighbors}, query.options());
+  at::Tensor work = grid_workspace(query, mvp_ball_query_workspace_bytes(query.size(0), query.size(1), key.size(1), radius, max_neighbors, dt));
   check_rc(mvp_ball_query(query.data_ptr(), key.data_ptr(), query.size(0), query.size(1), key.size(1), radius,
-                          max_neighbors, dt, index.data_ptr<int64_t>(), distance.data_ptr(), cur_stream()));
+                          max_neighbors, dt, index.data_ptr<int64_t>(), distance.data_ptr(),
+                          work.defined() ? work.data_ptr() : nullptr, cur_stream()));
   return {index, distance};
 }
 
@@ -98,8 +110,10 @@ std::vector<at::Tensor> knn_distance(const at::Tensor query, const at::Tensor ke
   c10::cuda::CUDAGuard guard(query.device());
   auto index = at::empty({query.size(0), query.size(1), k}, query.options().dtype(at::kLong));
   auto distance = at::empty({query.size(0), query.size(1), k}, query.options());
+  at::Tensor work = grid_workspace(query, mvp_knn_distance_workspace_bytes(query.size(0), query.size(1), key.size(1), dt));
   check_rc(mvp_knn_distance(query.data_ptr(), key.data_ptr(), query.size(0), query.size(1), key.size(1), k, dt,
-                            index.data_ptr<int64_t>(), distance.data_ptr(), cur_stream()));
+                            index.data_ptr<int64_t>(), distance.data_ptr(), work.defined() ? work.data_ptr() : nullptr,
+                            cur_stream()));
   return {index, distance};
 }
 

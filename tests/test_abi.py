@@ -39,9 +39,9 @@ def test_argument_errors_are_reported_without_a_gpu(built):
     assert rc == -1 and b'dim=2 or dim=3' in lib.mvp_last_error()
     rc = lib.mvp_fps(None, i64(1), i64(8), i64(3), i64(9), 0, None, None, None)
     assert rc == -1
-    rc = lib.mvp_knn_distance(None, None, i64(1), i64(4), i64(8), i64(5), 0, None, None, None)
+    rc = lib.mvp_knn_distance(None, None, i64(1), i64(4), i64(8), i64(5), 0, None, None, None, None)
     assert rc == -1 and b'3-NN' in lib.mvp_last_error()
-    rc = lib.mvp_knn_distance(None, None, i64(1), i64(4), i64(2), i64(3), 0, None, None, None)
+    rc = lib.mvp_knn_distance(None, None, i64(1), i64(4), i64(2), i64(3), 0, None, None, None, None)
     assert rc == -1
     lib.mvp_fps_workspace_bytes.restype = ctypes.c_int64
     assert lib.mvp_fps_workspace_bytes(i64(2), i64(8192), i64(3), i64(2048), 0) == 0

@@ -1,6 +1,6 @@
 """Per-source-line summary of an ncu report's source page (needs -lineinfo and --import-source on).
 
-  python tools/ncu_lines.py REPORT.ncu-rep KERNEL_ID [TOP]
+  python tools/ncu_lines.py REPORT.ncu-rep KERNEL_ID [TOP]   (KERNEL_ID = 0-based ID column of the raw page)
 
 Prints the lines of the kernel's CUDA source with the most warp-stall samples, the dominant stall reasons of
 each, and the executed warp-instruction count — the view used to decide what to optimise next.
@@ -14,7 +14,7 @@ import sys
 def main():
     rep, kid = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-id', ':::' + kid],
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-id', ':::%d' % (int(kid) + 1)],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = None
