@@ -65,9 +65,15 @@ void check_query_key(const at::Tensor &query, const at::Tensor &key) {
 }
 
 // workspace of the exact uniform-grid searches (csrc/point_grid.cu); MVPNET_B200_GRID=0 forces the exhaustive kernels
+static bool &grid_enabled() {
+  static bool enabled = [] { const char *e = getenv("MVPNET_B200_GRID"); return !(e && e[0] == '0'); }();
+  return enabled;
+}
+// tests flip this to compare the grid search with the exhaustive kernels in one process; returns the previous setting
+bool set_grid_search(bool on) { const bool was = grid_enabled(); grid_enabled() = on; return was; }
+
 at::Tensor grid_workspace(const at::Tensor &like, int64_t bytes) {
-  static const bool enabled = [] { const char *e = getenv("MVPNET_B200_GRID"); return !(e && e[0] == '0'); }();
-  if (!enabled || bytes <= 0) return at::Tensor();
+  if (!grid_enabled() || bytes <= 0) return at::Tensor();
   return at::empty({bytes}, like.options().dtype(at::kByte));
 }
 
@@ -491,6 +497,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "mvpnet_b200: sm_100a kernels behind the mvpnet.ops extension interface";
   m.def("abi_version", &mvp_abi_version);
   m.def("index_errors_fetch_and_clear", &index_errors_fetch_and_clear);
+  m.def("set_grid_search", &set_grid_search);
   auto fps = m.def_submodule("fps_cuda");
   fps.def("farthest_point_sample", &farthest_point_sample, "Farthest point sampling (CUDA)");
   auto bq = m.def_submodule("ball_query_cuda");
