@@ -213,6 +213,20 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
                                      const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
                                      const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream);
 
+/* ==== 3x3 / stride 1 / pad 1 convolution on the tensor cores (csrc/tc_conv.cu) ========================
+ * The convolutions of the 2D network in front of FeatureAggregation (mvpnet/models/unet_resnet34.py:9-125;
+ * called from MVPNet3D.forward, mvpnet_3d.py:94-99).  fp32 NHWC tensors:
+ *   out[n,y,x,:] = act(bias + sum_{ky,kx} W[:,:,ky,kx] . cat(x1, x2)[n, y+ky-1, x+kx-1, :] (+ residual[n,y,x,:]))
+ * x1 [N,H,W,C1], x2 [N,H,W,C2] or NULL (C2 = 0) — the UNet's cat([up, skip]) without the copy; residual
+ * [N,H,W,Cout] or NULL; relu != 0 applies max(., 0).  C1, C2, Cout multiples of 16 (Cout a multiple of 256 above
+ * 256).  Weights (BatchNorm folded by the caller) are split into bf16 hi = bf16(w), lo = bf16(w - hi) and stored
+ * in the kernel's operand order [Cout/Nt][Cin/16][tap = ky*3+kx][hi|lo][2][Nt][8], Nt = min(Cout, 256), element
+ * (nb, c, tap, hl, k8, n, e) = W_hl[nb*Nt + n, c*16 + k8*8 + e, ky, kx]: mvp_tc_conv3x3_weight_bytes() bytes. */
+int64_t mvp_tc_conv3x3_weight_bytes(int64_t Cin, int64_t Cout);
+int mvp_tc_conv3x3(const float *x1, int64_t C1, const float *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
+                   const void *w_packed, const float *bias, int64_t Cout, const float *residual, int relu,
+                   float *out, mvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

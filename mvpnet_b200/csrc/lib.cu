@@ -10,3 +10,4 @@
 #include "knn_pixels.cu"
 #include "fused_mlp.cu"
 #include "tc_mlp.cu"
+#include "tc_conv.cu"

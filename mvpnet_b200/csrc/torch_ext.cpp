@@ -398,6 +398,37 @@ struct TcChain {
   }
 };
 
+// 3x3 / stride 1 / pad 1 convolution, fp32 NHWC, on the tensor cores (csrc/tc_conv.cu).  x1 (N,H,W,C1) [+ x2 (N,H,W,C2):
+// the channel concatenation is never materialised], packed weights (see include/mvpnet_b200.h), bias (Cout),
+// optional residual (N,H,W,Cout) -> (N,H,W,Cout)
+at::Tensor tc_conv3x3(const at::Tensor x1, const c10::optional<at::Tensor> x2, const at::Tensor w_packed, const at::Tensor bias,
+                      const c10::optional<at::Tensor> residual, bool relu) {
+  CHECK_INPUT(x1); CHECK_F32(x1); CHECK_INPUT(w_packed); CHECK_INPUT(bias); CHECK_F32(bias);
+  TORCH_CHECK(x1.dim() == 4, "tc_conv3x3: x1 must be (N, H, W, C)");
+  const auto N = x1.size(0), H = x1.size(1), W = x1.size(2), C1 = x1.size(3), Cout = bias.size(0);
+  int64_t C2 = 0;
+  const float *p2 = nullptr, *pr = nullptr;
+  if (x2.has_value() && x2->defined()) {
+    CHECK_INPUT((*x2)); CHECK_F32((*x2));
+    TORCH_CHECK(x2->dim() == 4 && x2->size(0) == N && x2->size(1) == H && x2->size(2) == W, "tc_conv3x3: x2 must be (N, H, W, C2)");
+    C2 = x2->size(3);
+    p2 = x2->data_ptr<float>();
+  }
+  if (residual.has_value() && residual->defined()) {
+    CHECK_INPUT((*residual)); CHECK_F32((*residual));
+    TORCH_CHECK(residual->dim() == 4 && residual->size(0) == N && residual->size(1) == H && residual->size(2) == W &&
+                residual->size(3) == Cout, "tc_conv3x3: residual must be (N, H, W, Cout)");
+    pr = residual->data_ptr<float>();
+  }
+  TORCH_CHECK(w_packed.numel() * w_packed.element_size() == mvp_tc_conv3x3_weight_bytes(C1 + C2, Cout),
+              "tc_conv3x3: packed weights have the wrong size for ", C1 + C2, " -> ", Cout, " channels");
+  c10::cuda::CUDAGuard guard(x1.device());
+  auto out = at::empty({N, H, W, Cout}, x1.options());
+  check_rc(mvp_tc_conv3x3(x1.data_ptr<float>(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr,
+                          relu ? 1 : 0, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
 bool tc_chain_supported(const std::vector<int64_t> ks, const std::vector<int64_t> ns, int64_t mode) {
   mvp_tc_chain_t c = {};
   if (ks.empty() || ks.size() > MVP_MLP_MAX_LAYERS || ks.size() != ns.size()) return false;
@@ -522,6 +553,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("feature_propagation", &fused_feature_propagation, "3-NN interpolate + concat + MLP (CUDA)");
   fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
   fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
+  fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv, fp32 NHWC, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
   fz.def("tc_feature_aggregation", &tc_feature_aggregation, "pixel gather + relation + MLP (tcgen05) + sum/max");
   fz.def("tc_feature_propagation", &tc_feature_propagation, "3-NN interpolate + concat + MLP (tcgen05)");
 }

@@ -180,10 +180,10 @@ _CACHE = {}
 def _cached(module, key, build):
     sig = (key, tuple(int(t._version) for t in module.state_dict().values()),
            next(module.parameters()).device, module.training)
-    hit = _CACHE.get(id(module))
+    hit = _CACHE.get((id(module), key))
     if hit is None or hit[0] != sig:
         hit = (sig, build())
-        _CACHE[id(module)] = hit
+        _CACHE[(id(module), key)] = hit
     return hit[1]
 
 
@@ -349,6 +349,22 @@ def _folded_net2d(net):
     return _cached(net, 'net2d_folded', build)
 
 
+# 'tc'   : the UNet's 3x3 convolutions on this package's tcgen05 kernel (net2d.py), the rest on cuDNN channels-last
+# 'cudnn': the whole 2D network on cuDNN fp32 (BatchNorm folded)
+NET2D_BACKEND = os.environ.get('MVPNET_B200_NET2D', 'tc')
+
+
+def _tc_net2d(net):
+    from .unet import UNetResNet34
+    if NET2D_BACKEND != 'tc' or not isinstance(net, UNetResNet34):
+        return None
+
+    def build():
+        from .net2d import FastUNetResNet34
+        return FastUNetResNet34(net)
+    return _cached(net, 'net2d_tc', build)
+
+
 def mvpnet3d_forward(model, data_batch, overlap=True):
     """Fused MVPNet3D.forward (eval).  Everything that depends on coordinates only runs on a side stream
     while the 2D network runs on the main stream: the data side (depth unprojection + 2D->3D k-NN, when the
@@ -387,7 +403,11 @@ def mvpnet3d_forward(model, data_batch, overlap=True):
     else:
         rg, geo = coordinate_work()
     with _stage('net_2d'):
-        feat2d = _folded_net2d(model.net_2d).features(images.reshape(b * nv, *images.shape[2:]))
+        plan = _tc_net2d(model.net_2d)
+        if plan is not None:      # tcgen05 convolutions, fp32 NHWC end to end; (n, c, h, w) view with channel stride 1
+            feat2d = plan.features_nhwc(images.reshape(b * nv, *images.shape[2:])).permute(0, 3, 1, 2)
+        else:
+            feat2d = _folded_net2d(model.net_2d).features(images.reshape(b * nv, *images.shape[2:]))
     if FA_CHANNELS_LAST_COPY and feat2d.stride(1) != 1:
         with _stage('feat2d_to_channels_last'):
             feat2d = feat2d.contiguous(memory_format=torch.channels_last)   # one pass; pixel rows become 256-byte lines

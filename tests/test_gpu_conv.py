@@ -1,0 +1,74 @@
+"""tcgen05 3x3 convolution (csrc/tc_conv.cu) against torch conv2d in float64 on the same inputs, at every shape family
+the UNet uses (single / two-image tiles, partial tiles in x and y, concatenated inputs, residual, 1-2 output blocks),
+and the whole 2D-network plan against the module it replaces.  Tolerance: 2e-5 of max|reference| (bf16 hi/lo x 3
+products drop only the lo*lo term, ~2^-16 per product; the end-to-end logit bar is 1e-4)."""
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x1, x2, w, b, res, relu):
+    x = x1 if x2 is None else torch.cat([x1, x2], dim=3)
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    if res is not None:
+        y = y + res.double()
+    return y.clamp_min(0) if relu else y
+
+
+@pytest.mark.parametrize('n,h,w,c1,c2,cout,res,relu', [
+    (3, 64, 80, 64, 0, 64, True, True),        # layer1
+    (2, 128, 160, 64, 64, 64, False, True),    # decoder0: concat, largest tiles count
+    (3, 32, 40, 128, 0, 128, True, True),      # layer2
+    (3, 16, 20, 256, 0, 256, True, True),      # layer3: partial tile in x
+    (5, 8, 10, 512, 0, 512, True, True),       # layer4: two images per tile, odd image count, two output blocks
+    (3, 16, 20, 256, 256, 256, False, True),   # decoder3
+    (2, 30, 37, 16, 0, 16, False, False),      # ragged everything, no activation: signed outputs
+    (1, 5, 3, 32, 16, 48, True, False),
+    (7, 8, 8, 16, 0, 32, False, True),
+])
+def test_conv3x3_matches_float64(n, h, w, c1, c2, cout, res, relu):
+    from mvpnet_b200 import net2d
+    torch.manual_seed(n * 1000 + h)
+    dev = 'cuda'
+    x1 = torch.randn(n, h, w, c1, device=dev)
+    x2 = torch.randn(n, h, w, c2, device=dev) if c2 else None
+    wt = torch.randn(cout, c1 + c2, 3, 3, device=dev) / (3.0 * (c1 + c2) ** 0.5)
+    b = torch.randn(cout, device=dev)
+    r = torch.randn(n, h, w, cout, device=dev) if res else None
+    packed, bias = net2d.pack_conv3x3(wt, b)
+    got = net2d.conv3x3_nhwc(x1, packed, bias, x2=x2, residual=r, relu=relu)
+    want = ref_conv(x1, x2, wt, b, r, relu)
+    err = (got.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-5, err
+
+
+def test_conv3x3_errors():
+    from mvpnet_b200 import net2d
+    x = torch.randn(1, 8, 8, 24, device='cuda')
+    packed, bias = net2d.pack_conv3x3(torch.randn(16, 32, 3, 3), torch.zeros(16))
+    with pytest.raises(RuntimeError):
+        net2d.conv3x3_nhwc(x, packed.cuda(), bias.cuda())          # 24 channels: not a multiple of 16 / wrong weight size
+
+
+def test_fast_unet_matches_module():
+    from mvpnet_b200 import net2d, synthetic
+    from mvpnet_b200.unet import UNetResNet34
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        net = UNetResNet34(20, p=0.5, pretrained=False)
+    synthetic.fill_parameters(net, seed=4)
+    net = net.eval().cuda()
+    plan = net2d.FastUNetResNet34(net)
+    x = torch.randn(5, 3, 120, 160, device='cuda')
+    with torch.no_grad():
+        want = net.double().features(x.double())
+        got = plan.features_nhwc(x).permute(0, 3, 1, 2)
+    assert got.shape == want.shape
+    err = (got.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 5e-5, err
