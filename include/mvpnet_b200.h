@@ -215,17 +215,25 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
 
 /* ==== 3x3 / stride 1 / pad 1 convolution on the tensor cores (csrc/tc_conv.cu) ========================
  * The convolutions of the 2D network in front of FeatureAggregation (mvpnet/models/unet_resnet34.py:9-125;
- * called from MVPNet3D.forward, mvpnet_3d.py:94-99).  fp32 NHWC tensors:
+ * called from MVPNet3D.forward, mvpnet_3d.py:94-99):
  *   out[n,y,x,:] = act(bias + sum_{ky,kx} W[:,:,ky,kx] . cat(x1, x2)[n, y+ky-1, x+kx-1, :] (+ residual[n,y,x,:]))
- * x1 [N,H,W,C1], x2 [N,H,W,C2] or NULL (C2 = 0) — the UNet's cat([up, skip]) without the copy; residual
- * [N,H,W,Cout] or NULL; relu != 0 applies max(., 0).  C1, C2, Cout multiples of 16 (Cout a multiple of 256 above
- * 256).  Weights (BatchNorm folded by the caller) are split into bf16 hi = bf16(w), lo = bf16(w - hi) and stored
- * in the kernel's operand order [Cout/Nt][Cin/16][tap = ky*3+kx][hi|lo][2][Nt][8], Nt = min(Cout, 256), element
- * (nb, c, tap, hl, k8, n, e) = W_hl[nb*Nt + n, c*16 + k8*8 + e, ky, kx]: mvp_tc_conv3x3_weight_bytes() bytes. */
+ * Activations are "split-planar": every fp32 value v is carried as bf16 hi = bf16(v) and lo = bf16(v - hi); a tensor
+ * is two planes (hi, then lo), each [N][C/8][H][W][8] bf16 — or, when H <= 8, pair-interleaved
+ * [ceil(N/2)][C/8][H][2][W][8] (image 2p and 2p+1 share rows; a missing partner must read as zeros).
+ * mvp_planar_elems() gives the bf16 element count of both planes; mvp_split_planar / mvp_merge_planar convert from /
+ * to fp32 NHWC.  x2 may be NULL (C2 = 0): cat([up, skip]) without the copy.  residual (split-planar, Cout channels)
+ * may be NULL.  The result is written split-planar (out_planar) and / or as fp32 NHWC (out_nhwc); at least one.
+ * C1, C2, Cout multiples of 16 (Cout a multiple of 256 above 256).  Weights (BatchNorm folded by the caller) are
+ * split the same way and stored in the kernel's operand order [Cout/Nt][Cin/16][tap = ky*3+kx][hi|lo][2][Nt][8],
+ * Nt = min(Cout, 256), element (nb, c, tap, hl, k8, n, e) = W_hl[nb*Nt + n, c*16 + k8*8 + e, ky, kx]:
+ * mvp_tc_conv3x3_weight_bytes() bytes. */
 int64_t mvp_tc_conv3x3_weight_bytes(int64_t Cin, int64_t Cout);
-int mvp_tc_conv3x3(const float *x1, int64_t C1, const float *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
-                   const void *w_packed, const float *bias, int64_t Cout, const float *residual, int relu,
-                   float *out, mvp_stream_t stream);
+int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C);
+int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
+                   const void *w_packed, const float *bias, int64_t Cout, const void *residual, int relu,
+                   void *out_planar, float *out_nhwc, mvp_stream_t stream);
+int mvp_split_planar(const float *nhwc, int64_t N, int64_t H, int64_t W, int64_t C, void *planar, mvp_stream_t stream);
+int mvp_merge_planar(const void *planar, int64_t N, int64_t H, int64_t W, int64_t C, float *nhwc, mvp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,27 +1,35 @@
-// 3x3 / stride-1 / pad-1 convolution on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a, for the 2D
+// 3x3 / stride-1 / pad-1 convolution on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a, for the 2D
 // network in front of FeatureAggregation (reference: mvpnet/models/unet_resnet34.py:9-125 — 92 % of its multiply-adds
 // are such convolutions; MVPNet3D.forward, mvpnet_3d.py:94-99, spends ~90 % of a chunk's time there on fp32 cuDNN).
 //
 //   out[n,y,x,:] = act( bias + sum_{ky,kx} W[:, :, ky, kx] . in[n, y+ky-1, x+kx-1, :]  (+ residual[n,y,x,:]) )
 //
-// Tensors are fp32 NHWC; `in` may be the channel concatenation of two tensors (the UNet's cat([up, skip]),
-// unet_resnet34.py:96-112, never materialised).  BatchNorm is folded into W / bias by the caller (eval mode).
+// `in` may be the channel concatenation of two tensors (the UNet's cat([up, skip]), unet_resnet34.py:96-112, never
+// materialised).  BatchNorm is folded into W / bias by the caller (eval mode).
 //
-// Implicit GEMM, M = pixels, N = Cout, K = 9 x Cin, with the same precision scheme as tc_mlp.cu: every fp32
-// operand is split into bf16 hi + bf16 lo and each K-step issues three kind::f16 MMAs into one fp32 TMEM
-// accumulator (hi*hi + hi*lo + lo*hi).
+// Precision: as in tc_mlp.cu every fp32 value is carried as bf16 hi + bf16 lo (lo = bf16(v - hi)) and each K-step
+// issues three kind::f16 MMAs into one fp32 TMEM accumulator (hi*hi + hi*lo + lo*hi).  Activations LIVE in that form
+// between layers ("split-planar"): two planes (hi, lo), each [N][C/8][H][W][8] bf16 — the same 4 bytes per value as
+// fp32, but every 8-channel slab of an image is one contiguous H x W plane of 16-byte pixels, which is exactly the
+// unit of the UMMA K-major no-swizzle operand layout.  (For H <= 8 two images share a tile and the planes are stored
+// pair-interleaved, [N/2][C/8][H][2][W][8].)
 //
-//   * Tile = 128 output pixels = 16 rows x 8 columns of one image (or 8 x 8 of two images when H <= 8).  The A
-//     operand is the tile's input patch WITH its 1-pixel halo, staged once per 16-channel chunk in the canonical
-//     K-major no-swizzle UMMA layout with the pixel's x coordinate as the fastest index: a core matrix (8 rows x
-//     16 B) is 8 consecutive pixels of one image row, the stride between 8-row groups (SBO) is one halo row.  A
-//     filter tap (dy, dx) is then nothing but a different START ADDRESS of the same staged patch — nine MMAs
-//     groups read nine shifted views, no im2col copy exists anywhere.
-//   * Weights stream through a shared-memory ring as 1-D bulk async copies (one stage = one tap of one 16-channel
-//     chunk, hi | lo), and every stage is used by the TM (<= 4) pixel tiles a CTA keeps in flight (TM accumulators
-//     in TMEM), which keeps the L2 -> SM weight traffic at 1/TM of the tensor pipe's appetite.
-//   * Warp roles: 4 epilogue warps (TMEM -> bias / residual / ReLU -> global), 4 patch-producer warps (global fp32
-//     -> bf16 hi/lo -> shared), one MMA issuer lane, one weight-producer lane; mbarrier hand-offs throughout.
+// Implicit GEMM, M = pixels, N = Cout, K = 9 x Cin:
+//   * Tile = 128 output pixels = 16 rows x 8 columns of one image (8 x 8 of two images when H <= 8).  ONE TMA box
+//     load per (tile, 16-channel chunk, plane) brings the tile's input patch with its 1-pixel halo — zero padding is
+//     the TMA out-of-bounds fill — straight into the operand layout: a core matrix (8 rows x 16 B) is 8 consecutive
+//     pixels of an image row, the stride between 8-row groups (SBO) is one halo row.  A filter tap (dy, dx) is then
+//     nothing but a different START ADDRESS of the same staged patch: nine groups of MMAs read nine shifted views,
+//     no im2col copy exists anywhere and no thread ever touches the activations on their way in.
+//   * Weights stream through a shared-memory ring as 1-D bulk copies (one stage = one tap of one 16-channel chunk,
+//     hi | lo) and every stage is used by the TM (<= 4) pixel tiles a CTA keeps in flight (TM accumulators in TMEM),
+//     which keeps the L2 -> SM weight traffic at 1/TM of the tensor pipe's appetite.
+//   * TMEM holds two sets of accumulators where they fit (Cout <= 128): the epilogue of one tile group (TMEM ->
+//     bias / residual / ReLU -> split -> global) overlaps the MMAs of the next.
+//   * Warp roles: 4 epilogue warps, one MMA-issuer lane, one patch-producer lane (TMA), one weight-producer lane;
+//     mbarrier hand-offs throughout.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace mvp {
@@ -30,32 +38,36 @@ namespace tcc {
 using namespace tc;   // PTX wrappers of tc_mlp.cu
 
 constexpr int HC = 10;                        // halo columns: 8 + 2
-constexpr int HR_MAX = 20;                    // halo rows: 18 (one image) or 2 x 10 interleaved (two images)
-constexpr int UNITS = HC * HR_MAX;            // 16-byte units of one 8-channel slab of a patch
-constexpr int SLAB_BYTES = UNITS * 16;        // 3200: K-direction stride between core matrices (LBO)
-constexpr int SLOT_HALF = 2 * SLAB_BYTES;     // hi (or lo) part of a patch: 16 channels
+constexpr int SLOT_HALF = 2 * 200 * 16;       // hi (or lo) part of a patch: 2 slabs x (<= 20 halo rows x 10) x 16 B
 constexpr int SLOT_BYTES = 2 * SLOT_HALF;     // 12800
 constexpr int MAX_TM = 4;
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_THREADS = 128, PROD_THREADS = 128;
-constexpr int THREADS = EPI_THREADS + PROD_THREADS + 64;
+constexpr int MAX_ASETS = 3;
+constexpr int EPI_THREADS = 128;
+constexpr int THREADS = EPI_THREADS + 96;
 
 struct ConvArgs {
-  const float *x1, *x2;
+  CUtensorMap m1h, m1l, m2h, m2l;   // split-planar inputs: hi / lo plane of x1 and x2
   int C1, C2;
   int N, H, W;
-  const unsigned char *wp;     // [nb][chunk][tap][hi|lo][k8 (2)][n (Nt)][8] bf16
-  const float *bias, *res;
-  float *out;
+  const unsigned char *wp;          // [nb][chunk][tap][hi|lo][k8 (2)][n (Nt)][8] bf16
+  const float *bias;
+  const __nv_bfloat16 *res;         // split-planar residual (hi plane; lo at + plane_out) or null
+  __nv_bfloat16 *out_p;             // split-planar output or null
+  float *out_f;                     // fp32 NHWC output or null
+  long long plane_out;              // elements of one plane of res / out_p
   int Cout, Nt, NB;
   int relu;
-  int ipt;                     // images per tile: 1 (16 rows of one image) or 2 (8 rows of two images)
-  int TX, TY;                  // tiles per image along x / y
+  int ipt;                          // images per tile: 1 (16 rows of one image) or 2 (8 rows of two images)
+  int TX, TY;                       // tiles per image along x / y
   long long ntiles, ngroups;
-  int TM;                      // tiles per group (share every weight stage)
-  int nchunks;                 // (C1 + C2) / 16
-  int stages;
+  int TM;                           // tiles per group (share every weight stage)
+  int nacc;                         // accumulator sets in TMEM (1 or 2)
+  int asets;                        // patch ring depth (sets of TM slots)
+  int nchunks;                      // (C1 + C2) / 16
+  int stages;                       // weight ring depth
   int tmem_cols;
+  int dbg;                          // MVPNET_B200_CONV_DBG experiment bits (timing studies only; results are wrong)
 };
 
 struct TileCoord { int n, y0, x0; };
@@ -76,65 +88,113 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvArgs &a, long long t) 
   return c;
 }
 
+// element offset of pixel (n, y, x), slab c8 inside one split-planar plane
+__device__ __forceinline__ size_t planar_off(int n, int c8, int y, int x, int C8, int H, int W, int pair) {
+  if (pair) return (((((size_t)(n >> 1) * C8 + c8) * H + y) * 2 + (n & 1)) * W + x) * 8;
+  return ((((size_t)n * C8 + c8) * H + y) * W + x) * 8;
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+// one lane of the (converged) warp; ptxas then knows the guarded tcgen05 / bulk-copy instructions have one issuer
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+  return p != 0;
+}
+
+__device__ __forceinline__ void unpack8(const uint4 h, const uint4 l, float (&v)[8]) {   // hi + lo -> fp32
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-tc_conv3x3_kernel(const ConvArgs a) {
+tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // shared memory: [2 slot sets][TM slots] patches | [stages] weight ring | barriers
+  // shared memory: [asets][TM] patches | [stages] weight ring | barriers
   unsigned char *a_base = smem;
   const size_t stage_bytes = (size_t)64 * a.Nt;
-  unsigned char *b_base = a_base + (size_t)2 * a.TM * SLOT_BYTES;
+  unsigned char *b_base = a_base + (size_t)a.asets * a.TM * SLOT_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)a.stages * stage_bytes);
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 6);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2 * MAX_ASETS + 4);
   const uint32_t bar_bfull = smem_u32(bars), bar_bempty = smem_u32(bars + MAX_STAGES);
-  const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + 2);
-  const uint32_t bar_accfull = smem_u32(bars + 2 * MAX_STAGES + 4), bar_accempty = smem_u32(bars + 2 * MAX_STAGES + 5);
+  const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + MAX_ASETS);
+  const uint32_t bar_accfull = smem_u32(bars + 2 * MAX_STAGES + 2 * MAX_ASETS), bar_accempty = bar_accfull + 16;
 
   if (tid == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_afull + 8 * s, PROD_THREADS); mbar_init(bar_aempty + 8 * s, 1); }
-    mbar_init(bar_accfull, 1);
-    mbar_init(bar_accempty, EPI_THREADS);
+    for (int s = 0; s < MAX_ASETS; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const long long nworks = a.ngroups * a.NB;
-  const int rows_h = a.ipt == 1 ? 18 : 20;                  // halo rows in use
-  const int S = a.stages;
+  const int rows_h = a.ipt == 1 ? 18 : 20;                  // halo rows of a patch
+  const uint32_t slab_bytes = (uint32_t)(rows_h * HC * 16); // K-direction stride between core matrices (LBO)
+  const uint32_t S = (uint32_t)a.stages, AS = (uint32_t)a.asets, NA = (uint32_t)a.nacc;
+  const int pair = a.ipt == 2;
 
   if (warp < 4) {
     // =========================== epilogue: thread = TMEM lane = pixel ================================================
     const int row = warp * 32 + lane, g = row >> 3, xx = row & 7;
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int C8o = a.Cout >> 3;
     uint32_t it = 0;
     for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++it) {
       const int nb = (int)(w / a.ngroups);
       const long long group = w - (long long)nb * a.ngroups;
-      mbar_wait(bar_accfull, it & 1u);
+      const uint32_t set = it % NA;
+      mbar_wait(bar_accfull + 8 * set, (it / NA) & 1u);
       tc_fence_after();
       for (int t = 0; t < a.TM; ++t) {
         const long long tile = group * a.TM + t;
         if (tile >= a.ntiles) break;
         const TileCoord tc_ = tile_coord(a, tile);
-        const int img = a.ipt == 1 ? tc_.n : tc_.n + (g & 1);
-        const int y = a.ipt == 1 ? tc_.y0 + g : (g >> 1);
+        const int img = pair ? tc_.n + (g & 1) : tc_.n;
+        const int y = pair ? (g >> 1) : tc_.y0 + g;
         const int x = tc_.x0 + xx;
-        const bool ok = img < a.N && y < a.H && x < a.W;
-        const size_t pix = ((size_t)img * a.H + y) * a.W + x;
-        const size_t obase = pix * a.Cout + (size_t)nb * a.Nt;
+        const bool ok = img < a.N && y < a.H && x < a.W && !(a.dbg & 2);
+        const size_t slab_stride = (size_t)a.H * a.W * 8 * (pair ? 2 : 1);       // elements between slabs of one image
+        const size_t pbase = ok ? planar_off(img, nb * (a.Nt >> 3), y, x, C8o, a.H, a.W, pair) : 0;
+        const size_t fbase = ok ? (((size_t)img * a.H + y) * a.W + x) * a.Cout + (size_t)nb * a.Nt : 0;
+        const uint32_t t_acc = t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
         uint32_t rn[16];
-        tmem_ld16_issue(t_lane + (uint32_t)(t * a.Nt), rn);
+        uint4 rh[2], rl[2];
+        tmem_ld16_issue(t_acc, rn);
+        if (a.res != nullptr && ok) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + pbase + s * slab_stride));
+            rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + pbase + s * slab_stride));
+          }
+        }
         for (int c = 0; c < a.Nt; c += 16) {
           float v[16];
           tmem_ld_wait(rn);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
-          if (c + 16 < a.Nt) tmem_ld16_issue(t_lane + (uint32_t)(t * a.Nt + c + 16), rn);
+          if (c + 16 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 16), rn);
           const float4 *bp = reinterpret_cast<const float4 *>(a.bias + nb * a.Nt + c);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -143,141 +203,233 @@ tc_conv3x3_kernel(const ConvArgs a) {
           }
           if (ok) {
             if (a.res != nullptr) {
-              const float4 *rp = reinterpret_cast<const float4 *>(a.res + obase + c);
+              float r0[8], r1[8];
+              unpack8(rh[0], rl[0], r0);
+              unpack8(rh[1], rl[1], r1);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 rq = __ldg(rp + q);
-                v[4 * q] += rq.x; v[4 * q + 1] += rq.y; v[4 * q + 2] += rq.z; v[4 * q + 3] += rq.w;
+              for (int q = 0; q < 8; ++q) { v[q] += r0[q]; v[8 + q] += r1[q]; }
+              if (c + 16 < a.Nt) {           // next chunk's residual is in flight while this one is finished
+                const size_t o = pbase + (size_t)((c + 16) >> 3) * slab_stride;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                  rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + o + s * slab_stride));
+                  rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + o + s * slab_stride));
+                }
               }
             }
             if (a.relu) {
 #pragma unroll
               for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
             }
-            float4 *op = reinterpret_cast<float4 *>(a.out + obase + c);
+            if (a.out_p != nullptr) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int s = 0; s < 2; ++s) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) split_pair(v[8 * s + 2 * q], v[8 * s + 2 * q + 1], h[q], l[q]);
+                const size_t o = pbase + (size_t)((c >> 3) + s) * slab_stride;
+                *reinterpret_cast<uint4 *>(a.out_p + o) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4 *>(a.out_p + a.plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
+              }
+            }
+            if (a.out_f != nullptr) {
+              float4 *op = reinterpret_cast<float4 *>(a.out_f + fbase + c);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(bar_accempty);
+      mbar_arrive(bar_accempty + 8 * set);
     }
-  } else if (warp < 8) {
-    // =========================== patch producers: global fp32 NHWC -> bf16 hi / lo patches ===========================
-    const int ptid = tid - EPI_THREADS;
-    const int nunits = rows_h * HC * 2;                     // (pixel, 8-channel slab) units of one patch
-    uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
-      const long long group = w % a.ngroups;
-      for (int c = 0; c < a.nchunks; ++c, ++it) {
-        const uint32_t ss = it & 1u;
-        if (it >= 2) mbar_wait(bar_aempty + 8 * ss, ((it >> 1) - 1u) & 1u);
-        const int k0 = c * 16;
-        const float *src = k0 < a.C1 ? a.x1 : a.x2;
-        const int C = k0 < a.C1 ? a.C1 : a.C2, ch = k0 < a.C1 ? k0 : k0 - a.C1;
-        for (int t = 0; t < a.TM; ++t) {
-          const long long tile = group * a.TM + t;
-          if (tile >= a.ntiles) break;
-          const TileCoord tc_ = tile_coord(a, tile);
-          unsigned char *slot = a_base + (size_t)(ss * a.TM + t) * SLOT_BYTES;
-          constexpr int U = 4;                               // nunits <= 400 < 4 * 128
-          float4 lo4[U], hi4[U];
-          int offs[U];
-#pragma unroll
-          for (int i = 0; i < U; ++i) {
-            const int u = ptid + i * PROD_THREADS;
-            offs[i] = -1;
-            lo4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            hi4[i] = lo4[i];
-            if (u < nunits) {
-              const int k8 = u & 1, p = u >> 1, hr = p / HC, hc = p - hr * HC;
-              offs[i] = k8 * SLAB_BYTES + p * 16;
-              const int img = a.ipt == 1 ? tc_.n : tc_.n + (hr & 1);
-              const int y = a.ipt == 1 ? tc_.y0 + hr - 1 : (hr >> 1) - 1;
-              const int x = tc_.x0 + hc - 1;
-              if (img < a.N && y >= 0 && y < a.H && x >= 0 && x < a.W) {
-                const float4 *gp = reinterpret_cast<const float4 *>(src + (((size_t)img * a.H + y) * a.W + x) * C + ch + k8 * 8);
-                lo4[i] = __ldg(gp);
-                hi4[i] = __ldg(gp + 1);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < U; ++i) {
-            if (offs[i] >= 0) {
-              uint32_t h[4], l[4];
-              split_pair(lo4[i].x, lo4[i].y, h[0], l[0]);
-              split_pair(lo4[i].z, lo4[i].w, h[1], l[1]);
-              split_pair(hi4[i].x, hi4[i].y, h[2], l[2]);
-              split_pair(hi4[i].z, hi4[i].w, h[3], l[3]);
-              *reinterpret_cast<uint4 *>(slot + offs[i]) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4 *>(slot + SLOT_HALF + offs[i]) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_afull + 8 * ss);
-      }
-    }
-  } else if (warp == 8) {
+  } else if (warp == 4) {
     // =========================== MMA issuer ===========================================================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, a.Nt);
-      uint32_t a_it = 0, b_it = 0, w_it = 0;
-      for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++w_it) {
-        const long long group = w % a.ngroups;
-        const long long left = a.ntiles - group * a.TM;
-        const int nt = left < a.TM ? (int)left : a.TM;
-        if (w_it > 0) { mbar_wait(bar_accempty, (w_it - 1u) & 1u); tc_fence_after(); }
-        for (int c = 0; c < a.nchunks; ++c, ++a_it) {
-          const uint32_t ss = a_it & 1u;
-          mbar_wait(bar_afull + 8 * ss, (a_it >> 1) & 1u);
-          tc_fence_after();
-          for (int tap = 0; tap < 9; ++tap, ++b_it) {
-            const uint32_t s = b_it % (uint32_t)S;
-            mbar_wait(bar_bfull + 8 * s, (b_it / (uint32_t)S) & 1u);
-            tc_fence_after();
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            const uint32_t aoff = (uint32_t)(((a.ipt * (1 + dy)) * HC + (1 + dx)) * 16);
-            const uint32_t b_hi = smem_u32(b_base + (size_t)s * stage_bytes), b_lo = b_hi + 32u * (uint32_t)a.Nt;
-            const uint64_t bh = make_desc(b_hi, (uint32_t)a.Nt * 16u, 128), bl = make_desc(b_lo, (uint32_t)a.Nt * 16u, 128);
-            for (int t = 0; t < nt; ++t) {
-              const uint32_t a_hi = smem_u32(a_base + (size_t)(ss * a.TM + t) * SLOT_BYTES) + aoff, a_lo = a_hi + SLOT_HALF;
-              const uint64_t ah = make_desc(a_hi, SLAB_BYTES, HC * 16), al = make_desc(a_lo, SLAB_BYTES, HC * 16);
-              const uint32_t d = tmem_base + (uint32_t)(t * a.Nt);
+    // The WHOLE warp walks the loops (every value is warp-uniform, so descriptors live in uniform registers) and one
+    // elected lane issues; a loop under `if (lane == 0)` makes ptxas wrap every tcgen05 instruction in a
+    // thread-by-thread broadcast loop, which costs more than the MMAs of a narrow layer take to execute.
+    const uint32_t idesc = make_idesc(128, a.Nt);
+    const uint32_t a_s = smem_u32(a_base), b_s = smem_u32(b_base);
+    const uint64_t adesc0 = make_desc(0, slab_bytes, HC * 16), bdesc0 = make_desc(0, (uint32_t)a.Nt * 16u, 128);
+    uint32_t a_it = 0, b_it = 0, w_it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++w_it) {
+      const long long group = w % a.ngroups;
+      const long long left = a.ntiles - group * a.TM;
+      const int nt = left < a.TM ? (int)left : a.TM;
+      const uint32_t set = w_it % NA;
+      if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, ((w_it / NA) - 1u) & 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + set * (uint32_t)(a.TM * a.Nt);
+      for (int c = 0; c < a.nchunks; ++c, ++a_it) {
+        const uint32_t ss = a_it % AS;
+        mbar_wait(bar_afull + 8 * ss, (a_it / AS) & 1u);
+        const uint32_t a_set = a_s + ss * (uint32_t)(a.TM * SLOT_BYTES);
+        for (int tap = 0; tap < 9; ++tap, ++b_it) {
+          const uint32_t s = b_it % S;
+          mbar_wait(bar_bfull + 8 * s, (b_it / S) & 1u);
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          const uint32_t a_tap = a_set + (uint32_t)(((a.ipt * (1 + dy)) * HC + (1 + dx)) * 16);
+          const uint32_t b_hi = b_s + s * (uint32_t)stage_bytes;
+          const uint64_t bh = bdesc0 | (uint64_t)((b_hi >> 4) & 0x3fffu), bl = bdesc0 | (uint64_t)(((b_hi + 32u * (uint32_t)a.Nt) >> 4) & 0x3fffu);
+          if (elect_one()) {
+            for (int t = 0; t < nt && !(a.dbg & 16); ++t) {
+              const uint32_t a_hi = a_tap + (uint32_t)(t * SLOT_BYTES);
+              const uint64_t ah = adesc0 | (uint64_t)((a_hi >> 4) & 0x3fffu), al = adesc0 | (uint64_t)(((a_hi + SLOT_HALF) >> 4) & 0x3fffu);
+              const uint32_t d = d0 + (uint32_t)(t * a.Nt);
               umma_bf16(d, ah, bh, idesc, (c == 0 && tap == 0) ? 0u : 1u);
-              umma_bf16(d, ah, bl, idesc, 1u);
-              umma_bf16(d, al, bh, idesc, 1u);
+              if (!(a.dbg & 1)) {
+                umma_bf16(d, ah, bl, idesc, 1u);
+                umma_bf16(d, al, bh, idesc, 1u);
+              }
             }
             umma_commit(bar_bempty + 8 * s);
           }
-          umma_commit(bar_aempty + 8 * ss);
+          __syncwarp();
         }
-        umma_commit(bar_accfull);
+        if (elect_one()) umma_commit(bar_aempty + 8 * ss);
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(bar_accfull + 8 * set);
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // =========================== patch producer: one TMA box per (tile, chunk, plane) ================================
+    const uint32_t box_bytes = 2u * slab_bytes;
+    const uint32_t a_s = smem_u32(a_base);
+    uint32_t it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
+      const long long group = w % a.ngroups;
+      const long long left = a.ntiles - group * a.TM;
+      const int nt = left < a.TM ? (int)left : a.TM;
+      for (int c = 0; c < a.nchunks; ++c, ++it) {
+        const uint32_t ss = it % AS;
+        if (it >= AS) mbar_wait(bar_aempty + 8 * ss, ((it / AS) - 1u) & 1u);
+        const int k0 = c * 16;
+        const bool first = k0 < a.C1;
+        const CUtensorMap *mh = first ? &a.m1h : &a.m2h, *ml = first ? &a.m1l : &a.m2l;
+        const int C8 = (first ? a.C1 : a.C2) >> 3, s0 = (first ? k0 : k0 - a.C1) >> 3;
+        if (elect_one()) {
+          mbar_expect_tx(bar_afull + 8 * ss, (uint32_t)nt * 2u * box_bytes);
+          for (int t = 0; t < nt; ++t) {
+            const TileCoord tc_ = tile_coord(a, group * a.TM + t);
+            const uint32_t dst = a_s + (ss * (uint32_t)a.TM + (uint32_t)t) * SLOT_BYTES;
+            if (!pair) {                 // dims (8 * W, H, C8 * N)
+              tma_load_3d(dst, mh, (tc_.x0 - 1) * 8, tc_.y0 - 1, tc_.n * C8 + s0, bar_afull + 8 * ss);
+              tma_load_3d(dst + SLOT_HALF, ml, (tc_.x0 - 1) * 8, tc_.y0 - 1, tc_.n * C8 + s0, bar_afull + 8 * ss);
+            } else {                     // dims (8 * W, 2, H, C8 * N/2)
+              tma_load_4d(dst, mh, (tc_.x0 - 1) * 8, 0, -1, (tc_.n >> 1) * C8 + s0, bar_afull + 8 * ss);
+              tma_load_4d(dst + SLOT_HALF, ml, (tc_.x0 - 1) * 8, 0, -1, (tc_.n >> 1) * C8 + s0, bar_afull + 8 * ss);
+            }
+          }
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // =========================== weight producer ======================================================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
-        const int nb = (int)(w / a.ngroups);
-        const unsigned char *wsrc = a.wp + (size_t)nb * a.nchunks * 9 * stage_bytes;
-        for (int j = 0; j < a.nchunks * 9; ++j, ++it) {
-          const uint32_t s = it % (uint32_t)S;
-          if (it >= (uint32_t)S) mbar_wait(bar_bempty + 8 * s, ((it / (uint32_t)S) - 1u) & 1u);
-          mbar_expect_tx(bar_bfull + 8 * s, (uint32_t)stage_bytes);
-          bulk_g2s(smem_u32(b_base + (size_t)s * stage_bytes), wsrc + (size_t)j * stage_bytes, (uint32_t)stage_bytes, bar_bfull + 8 * s);
+    const uint32_t b_s = smem_u32(b_base);
+    uint32_t it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
+      const int nb = (int)(w / a.ngroups);
+      const unsigned char *wsrc = a.wp + (size_t)nb * a.nchunks * 9 * stage_bytes;
+      for (int j = 0; j < a.nchunks * 9; ++j, ++it) {
+        const uint32_t s = it % S;
+        if (it >= S) mbar_wait(bar_bempty + 8 * s, ((it / S) - 1u) & 1u);
+        if (elect_one()) {
+          const uint32_t nbytes = (a.dbg & 4) ? 16u : (uint32_t)stage_bytes;
+          mbar_expect_tx(bar_bfull + 8 * s, nbytes);
+          bulk_g2s(b_s + s * (uint32_t)stage_bytes, wsrc + (size_t)j * stage_bytes, nbytes, bar_bfull + 8 * s);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// ---- split-planar <-> fp32 NHWC (the boundary to the layers that still run on cuDNN) --------------------------------
+// thread = (n, slab, y, x), x fastest: planar side coalesced 16-byte units, NHWC side one 32-byte sector per thread
+__global__ void __launch_bounds__(256)
+split_planar_kernel(const float *__restrict__ src, int N, int H, int W, int C, int pair, __nv_bfloat16 *__restrict__ dst, long long plane) {
+  const int C8 = C >> 3;
+  const long long total = (long long)N * C8 * H * W;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H); r /= H;
+    const int c8 = (int)(r % C8);
+    const int n = (int)(r / C8);
+    const float4 *p = reinterpret_cast<const float4 *>(src + (((size_t)n * H + y) * W + x) * C + c8 * 8);
+    const float4 u = __ldg(p), v = __ldg(p + 1);
+    uint32_t h[4], l[4];
+    split_pair(u.x, u.y, h[0], l[0]); split_pair(u.z, u.w, h[1], l[1]);
+    split_pair(v.x, v.y, h[2], l[2]); split_pair(v.z, v.w, h[3], l[3]);
+    const size_t o = planar_off(n, c8, y, x, C8, H, W, pair);
+    *reinterpret_cast<uint4 *>(dst + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(dst + plane + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+merge_planar_kernel(const __nv_bfloat16 *__restrict__ src, long long plane, int N, int H, int W, int C, int pair, float *__restrict__ dst) {
+  const int C8 = C >> 3;
+  const long long total = (long long)N * C8 * H * W;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H); r /= H;
+    const int c8 = (int)(r % C8);
+    const int n = (int)(r / C8);
+    const size_t o = planar_off(n, c8, y, x, C8, H, W, pair);
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4 *>(src + o)), __ldg(reinterpret_cast<const uint4 *>(src + plane + o)), v);
+    float4 *p = reinterpret_cast<float4 *>(dst + (((size_t)n * H + y) * W + x) * C + c8 * 8);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ---- host -----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// tensor map over one plane of a split-planar activation tensor; box = one tile's patch of one 16-channel chunk
+static int make_plane_map(CUtensorMap *m, const void *plane, int64_t N, int64_t H, int64_t W, int64_t C, int pair) {
+  EncodeTiledFn enc = encode_tiled();
+  MVP_REQUIRE(enc != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv3x3: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t C8 = (cuuint64_t)(C / 8);
+  CUresult r;
+  // the 8 channels of a slab and the pixels of an image row are contiguous: one dimension, so that a box row is one
+  // 160-byte request (a 16-byte innermost dimension costs one TMA request per pixel and starves the tensor pipe)
+  if (!pair) {
+    const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, C8 * (cuuint64_t)N};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t box[3] = {HC * 8, 18, 2}, es[3] = {1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, 2, (cuuint64_t)H, C8 * (cuuint64_t)((N + 1) / 2)};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)2 * W * 16, (cuuint64_t)H * 2 * W * 16};
+    const cuuint32_t box[4] = {HC * 8, 2, 10, 2}, es[4] = {1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  MVP_REQUIRE(r == CUDA_SUCCESS, MVP_ERR_INVALID_ARG, "tc_conv3x3: cuTensorMapEncodeTiled failed (%d) for N=%lld H=%lld W=%lld C=%lld", (int)r,
+              (long long)N, (long long)H, (long long)W, (long long)C);
+  return 0;
 }
 
 }  // namespace tcc
@@ -285,9 +437,15 @@ tc_conv3x3_kernel(const ConvArgs a) {
 
 extern "C" int64_t mvp_tc_conv3x3_weight_bytes(int64_t Cin, int64_t Cout) { return Cin * Cout * 9 * 4; }
 
-extern "C" int mvp_tc_conv3x3(const float *x1, int64_t C1, const float *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
-                              const void *w_packed, const float *bias, int64_t Cout, const float *residual, int relu,
-                              float *out, mvp_stream_t stream) {
+// elements (bf16) of a split-planar tensor: both planes
+extern "C" int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C) {
+  const int64_t n = H <= 8 ? (N + 1) / 2 * 2 : N;
+  return 2 * n * C * H * W;
+}
+
+extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
+                              const void *w_packed, const float *bias, int64_t Cout, const void *residual, int relu,
+                              void *out_planar, float *out_nhwc, mvp_stream_t stream) {
   using namespace mvp;
   MVP_REQUIRE(N >= 0 && H > 0 && W > 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: bad sizes");
   MVP_REQUIRE(C1 > 0 && C1 % 16 == 0 && C2 >= 0 && C2 % 16 == 0, MVP_ERR_UNSUPPORTED, "tc_conv3x3: input channels must be multiples of 16");
@@ -295,40 +453,95 @@ extern "C" int mvp_tc_conv3x3(const float *x1, int64_t C1, const float *x2, int6
               "tc_conv3x3: output channels must be a multiple of 16, and of 256 above 256");
   MVP_REQUIRE(N * H * W < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv3x3: more than 2^31 pixels");
   if (N == 0) return 0;
-  MVP_REQUIRE(x1 && w_packed && bias && out && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3: null pointer");
-  MVP_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)out) & 15) == 0,
-              MVP_ERR_INVALID_ARG, "tc_conv3x3: pointers must be 16-byte aligned");
+  MVP_REQUIRE(x1 && w_packed && bias && (out_planar || out_nhwc) && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3: null pointer");
+  MVP_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)out_planar |
+                (uintptr_t)out_nhwc) & 15) == 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: pointers must be 16-byte aligned");
   tcc::ConvArgs a = {};
-  a.x1 = x1; a.x2 = x2; a.C1 = (int)C1; a.C2 = (int)C2; a.N = (int)N; a.H = (int)H; a.W = (int)W;
-  a.wp = (const unsigned char *)w_packed; a.bias = bias; a.res = residual; a.out = out; a.relu = relu;
+  const int pair = H <= 8 ? 1 : 0;
+  const int64_t Np = pair ? (N + 1) / 2 * 2 : N;
+  if (int rc = tcc::make_plane_map(&a.m1h, x1, N, H, W, C1, pair)) return rc;
+  if (int rc = tcc::make_plane_map(&a.m1l, (const __nv_bfloat16 *)x1 + Np * C1 * H * W, N, H, W, C1, pair)) return rc;
+  if (C2 > 0) {
+    if (int rc = tcc::make_plane_map(&a.m2h, x2, N, H, W, C2, pair)) return rc;
+    if (int rc = tcc::make_plane_map(&a.m2l, (const __nv_bfloat16 *)x2 + Np * C2 * H * W, N, H, W, C2, pair)) return rc;
+  }
+  a.C1 = (int)C1; a.C2 = (int)C2; a.N = (int)N; a.H = (int)H; a.W = (int)W;
+  a.wp = (const unsigned char *)w_packed; a.bias = bias; a.res = (const __nv_bfloat16 *)residual;
+  a.out_p = (__nv_bfloat16 *)out_planar; a.out_f = out_nhwc; a.plane_out = Np * Cout * H * W; a.relu = relu;
   a.Cout = (int)Cout; a.Nt = Cout <= 256 ? (int)Cout : 256; a.NB = a.Cout / a.Nt;
-  a.ipt = H <= 8 ? 2 : 1;
+  a.ipt = pair ? 2 : 1;
   a.TX = (int)((W + 7) / 8);
-  a.TY = a.ipt == 1 ? (int)((H + 15) / 16) : 1;
-  a.ntiles = a.ipt == 1 ? N * a.TX * a.TY : ((N + 1) / 2) * a.TX;
-  a.TM = 512 / a.Nt < tcc::MAX_TM ? 512 / a.Nt : tcc::MAX_TM;
+  a.TY = pair ? 1 : (int)((H + 15) / 16);
+  a.ntiles = pair ? (Np / 2) * a.TX : N * a.TX * a.TY;
+  // accumulators: two sets (epilogue overlaps the next group's MMAs) where 2 x TM x Nt columns fit TMEM
+  a.TM = a.Nt <= 64 ? 4 : 2;
+  a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
   // spread over the SMs before stacking tiles on one CTA
   while (a.TM > 1 && (a.ntiles + a.TM - 1) / a.TM * a.NB < sm_count()) a.TM >>= 1;
   a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
   a.nchunks = (int)((C1 + C2) / 16);
   a.tmem_cols = 32;
-  while (a.tmem_cols < a.TM * a.Nt) a.tmem_cols <<= 1;
-  const size_t fixed = (size_t)2 * a.TM * tcc::SLOT_BYTES + 512;
+  while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
+  a.asets = tcc::MAX_ASETS;
   a.stages = tcc::MAX_STAGES;
-  while (a.stages > 2 && fixed + (size_t)a.stages * 64 * a.Nt > tc::SMEM_CAP) --a.stages;
-  const size_t smem = fixed + (size_t)a.stages * 64 * a.Nt;
+  {
+    const char *e = getenv("MVPNET_B200_CONV_DBG");
+    a.dbg = e ? atoi(e) : 0;
+    const char *st = getenv("MVPNET_B200_CONV_STAGES");
+    if (st && atoi(st) >= 2 && atoi(st) <= tcc::MAX_STAGES) a.stages = atoi(st);
+    const char *tm = getenv("MVPNET_B200_CONV_TM");
+    if (tm && atoi(tm) >= 1 && atoi(tm) <= tcc::MAX_TM && atoi(tm) * a.Nt <= 512) {
+      a.TM = atoi(tm);
+      a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
+      a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
+      a.tmem_cols = 32;
+      while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
+    }
+  }
+  auto smem_of = [&]() { return (size_t)a.asets * a.TM * tcc::SLOT_BYTES + (size_t)a.stages * 64 * a.Nt + 512; };
+  while (a.stages > 4 && smem_of() > tc::SMEM_CAP) --a.stages;
+  while (a.asets > 2 && smem_of() > tc::SMEM_CAP) --a.asets;
+  const size_t smem = smem_of();
   MVP_REQUIRE(smem <= tc::SMEM_CAP, MVP_ERR_UNSUPPORTED, "tc_conv3x3: shared memory budget exceeded");
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_conv3x3: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;
-  // one CTA per SM (TMEM: up to 512 columns each); smaller shared-memory footprints could co-reside, which the
-  // full-width TMEM allocation of a second CTA would turn into a dead-lock, so the grid never exceeds the SM count
-  long long grid = sm_count();
+  long long grid = sm_count();              // persistent, one CTA per SM
   if (grid > nworks) grid = nworks;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
   if (debug)
-    fprintf(stderr, "[tc_conv3x3] N=%d H=%d W=%d Cin=%d+%d Cout=%d Nt=%d ipt=%d tiles=%lld TM=%d works=%lld stages=%d smem=%zu tmem=%d\n",
-            a.N, a.H, a.W, a.C1, a.C2, a.Cout, a.Nt, a.ipt, a.ntiles, a.TM, nworks, a.stages, smem, a.tmem_cols);
+    fprintf(stderr, "[tc_conv3x3] N=%d H=%d W=%d Cin=%d+%d Cout=%d Nt=%d ipt=%d tiles=%lld TM=%d nacc=%d works=%lld asets=%d stages=%d smem=%zu tmem=%d\n",
+            a.N, a.H, a.W, a.C1, a.C2, a.Cout, a.Nt, a.ipt, a.ntiles, a.TM, a.nacc, nworks, a.asets, a.stages, smem, a.tmem_cols);
   tcc::tc_conv3x3_kernel<<<(unsigned)grid, tcc::THREADS, smem, (cudaStream_t)stream>>>(a);
   return launch_status("tc_conv3x3");
+}
+
+extern "C" int mvp_split_planar(const float *nhwc, int64_t N, int64_t H, int64_t W, int64_t C, void *planar, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(C > 0 && C % 8 == 0 && N >= 0 && H > 0 && W > 0, MVP_ERR_INVALID_ARG, "split_planar: bad sizes (C must be a multiple of 8)");
+  if (N == 0) return 0;
+  MVP_REQUIRE(nhwc && planar, MVP_ERR_NULL, "split_planar: null pointer");
+  const int pair = H <= 8 ? 1 : 0;
+  const int64_t Np = pair ? (N + 1) / 2 * 2 : N, plane = Np * C * H * W;
+  if (Np != N) {   // the missing partner image of the last pair reads as zeros
+    cudaError_t e = cudaMemsetAsync(planar, 0, (size_t)plane * 4, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("split_planar: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const long long total = N * (C / 8) * H * W;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
+  tcc::split_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nhwc, (int)N, (int)H, (int)W, (int)C, pair, (__nv_bfloat16 *)planar, plane);
+  return launch_status("split_planar");
+}
+
+extern "C" int mvp_merge_planar(const void *planar, int64_t N, int64_t H, int64_t W, int64_t C, float *nhwc, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(C > 0 && C % 8 == 0 && N >= 0 && H > 0 && W > 0, MVP_ERR_INVALID_ARG, "merge_planar: bad sizes (C must be a multiple of 8)");
+  if (N == 0) return 0;
+  MVP_REQUIRE(nhwc && planar, MVP_ERR_NULL, "merge_planar: null pointer");
+  const int pair = H <= 8 ? 1 : 0;
+  const int64_t Np = pair ? (N + 1) / 2 * 2 : N, plane = Np * C * H * W;
+  const long long total = N * (C / 8) * H * W;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
+  tcc::merge_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)planar, plane, (int)N, (int)H, (int)W, (int)C, pair, nhwc);
+  return launch_status("merge_planar");
 }

@@ -398,34 +398,62 @@ struct TcChain {
   }
 };
 
-// 3x3 / stride 1 / pad 1 convolution, fp32 NHWC, on the tensor cores (csrc/tc_conv.cu).  x1 (N,H,W,C1) [+ x2 (N,H,W,C2):
-// the channel concatenation is never materialised], packed weights (see include/mvpnet_b200.h), bias (Cout),
-// optional residual (N,H,W,Cout) -> (N,H,W,Cout)
-at::Tensor tc_conv3x3(const at::Tensor x1, const c10::optional<at::Tensor> x2, const at::Tensor w_packed, const at::Tensor bias,
-                      const c10::optional<at::Tensor> residual, bool relu) {
-  CHECK_INPUT(x1); CHECK_F32(x1); CHECK_INPUT(w_packed); CHECK_INPUT(bias); CHECK_F32(bias);
-  TORCH_CHECK(x1.dim() == 4, "tc_conv3x3: x1 must be (N, H, W, C)");
-  const auto N = x1.size(0), H = x1.size(1), W = x1.size(2), C1 = x1.size(3), Cout = bias.size(0);
-  int64_t C2 = 0;
-  const float *p2 = nullptr, *pr = nullptr;
+// ---- 2D network on the tensor cores (csrc/tc_conv.cu).  Split-planar activations are flat bf16 tensors of
+// mvp_planar_elems(N, H, W, C) elements; their logical shape travels beside them.
+at::Tensor split_planar(const at::Tensor nhwc) {
+  CHECK_INPUT(nhwc); CHECK_F32(nhwc);
+  TORCH_CHECK(nhwc.dim() == 4, "split_planar: input must be fp32 (N, H, W, C)");
+  const auto N = nhwc.size(0), H = nhwc.size(1), W = nhwc.size(2), C = nhwc.size(3);
+  c10::cuda::CUDAGuard guard(nhwc.device());
+  auto out = at::empty({mvp_planar_elems(N, H, W, C)}, nhwc.options().dtype(at::kBFloat16));
+  check_rc(mvp_split_planar(nhwc.data_ptr<float>(), N, H, W, C, out.data_ptr(), cur_stream()));
+  return out;
+}
+
+at::Tensor merge_planar(const at::Tensor planar, int64_t N, int64_t H, int64_t W, int64_t C) {
+  CHECK_INPUT(planar);
+  TORCH_CHECK(planar.scalar_type() == at::kBFloat16 && planar.numel() == mvp_planar_elems(N, H, W, C), "merge_planar: wrong planar size");
+  c10::cuda::CUDAGuard guard(planar.device());
+  auto out = at::empty({N, H, W, C}, planar.options().dtype(at::kFloat));
+  check_rc(mvp_merge_planar(planar.data_ptr(), N, H, W, C, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
+// x1 (C1 channels) [+ x2 (C2 channels)] split-planar, packed weights, bias (Cout), optional split-planar residual
+// -> split-planar (N,H,W,Cout), or fp32 NHWC when nhwc_out
+at::Tensor tc_conv3x3(const at::Tensor x1, int64_t C1, const c10::optional<at::Tensor> x2, int64_t C2, int64_t N, int64_t H, int64_t W,
+                      const at::Tensor w_packed, const at::Tensor bias, const c10::optional<at::Tensor> residual, bool relu, bool nhwc_out) {
+  CHECK_INPUT(x1); CHECK_INPUT(w_packed); CHECK_INPUT(bias); CHECK_F32(bias);
+  const auto Cout = bias.size(0);
+  TORCH_CHECK(x1.scalar_type() == at::kBFloat16 && x1.numel() == mvp_planar_elems(N, H, W, C1), "tc_conv3x3: x1 is not split-planar (N,H,W,C1)");
+  const void *p2 = nullptr, *pr = nullptr;
   if (x2.has_value() && x2->defined()) {
-    CHECK_INPUT((*x2)); CHECK_F32((*x2));
-    TORCH_CHECK(x2->dim() == 4 && x2->size(0) == N && x2->size(1) == H && x2->size(2) == W, "tc_conv3x3: x2 must be (N, H, W, C2)");
-    C2 = x2->size(3);
-    p2 = x2->data_ptr<float>();
+    CHECK_INPUT((*x2));
+    TORCH_CHECK(x2->scalar_type() == at::kBFloat16 && x2->numel() == mvp_planar_elems(N, H, W, C2), "tc_conv3x3: x2 is not split-planar (N,H,W,C2)");
+    p2 = x2->data_ptr();
+  } else {
+    TORCH_CHECK(C2 == 0, "tc_conv3x3: C2 given without x2");
   }
   if (residual.has_value() && residual->defined()) {
-    CHECK_INPUT((*residual)); CHECK_F32((*residual));
-    TORCH_CHECK(residual->dim() == 4 && residual->size(0) == N && residual->size(1) == H && residual->size(2) == W &&
-                residual->size(3) == Cout, "tc_conv3x3: residual must be (N, H, W, Cout)");
-    pr = residual->data_ptr<float>();
+    CHECK_INPUT((*residual));
+    TORCH_CHECK(residual->scalar_type() == at::kBFloat16 && residual->numel() == mvp_planar_elems(N, H, W, Cout),
+                "tc_conv3x3: residual is not split-planar (N,H,W,Cout)");
+    pr = residual->data_ptr();
   }
   TORCH_CHECK(w_packed.numel() * w_packed.element_size() == mvp_tc_conv3x3_weight_bytes(C1 + C2, Cout),
               "tc_conv3x3: packed weights have the wrong size for ", C1 + C2, " -> ", Cout, " channels");
   c10::cuda::CUDAGuard guard(x1.device());
-  auto out = at::empty({N, H, W, Cout}, x1.options());
-  check_rc(mvp_tc_conv3x3(x1.data_ptr<float>(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr,
-                          relu ? 1 : 0, out.data_ptr<float>(), cur_stream()));
+  at::Tensor out;
+  if (nhwc_out) {
+    out = at::empty({N, H, W, Cout}, x1.options().dtype(at::kFloat));
+    check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
+                            nullptr, out.data_ptr<float>(), cur_stream()));
+  } else {
+    // an odd image count leaves a partner-less image in the last pair of a pair-interleaved tensor: keep it zero
+    out = (H <= 8 && (N & 1)) ? at::zeros({mvp_planar_elems(N, H, W, Cout)}, x1.options()) : at::empty({mvp_planar_elems(N, H, W, Cout)}, x1.options());
+    check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
+                            out.data_ptr(), nullptr, cur_stream()));
+  }
   return out;
 }
 
@@ -553,7 +581,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("feature_propagation", &fused_feature_propagation, "3-NN interpolate + concat + MLP (CUDA)");
   fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
   fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
-  fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv, fp32 NHWC, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
+  fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv on split-planar activations, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
+  fz.def("split_planar", &split_planar, "fp32 NHWC -> split-planar bf16 hi/lo");
+  fz.def("merge_planar", &merge_planar, "split-planar bf16 hi/lo -> fp32 NHWC");
   fz.def("tc_feature_aggregation", &tc_feature_aggregation, "pixel gather + relation + MLP (tcgen05) + sum/max");
   fz.def("tc_feature_propagation", &tc_feature_propagation, "3-NN interpolate + concat + MLP (tcgen05)");
 }

@@ -48,12 +48,33 @@ def pack_conv3x3(weight, bias):
     return x.view(torch.uint8).reshape(-1).contiguous(), bias.float().contiguous()
 
 
-def conv3x3_nhwc(x1, packed, bias, x2=None, residual=None, relu=True):
-    return load_ext().fused_cuda.tc_conv3x3(x1, x2, packed, bias, residual, relu)
+class Planar:
+    """A split-planar activation tensor (see include/mvpnet_b200.h): flat bf16 storage + logical (N, H, W, C)."""
+    __slots__ = ('data', 'n', 'h', 'w', 'c')
+
+    def __init__(self, data, n, h, w, c):
+        self.data, self.n, self.h, self.w, self.c = data, n, h, w, c
+
+    @staticmethod
+    def from_nhwc(x):
+        """fp32 (N, H, W, C) contiguous -> split-planar."""
+        n, h, w, c = x.shape
+        return Planar(load_ext().fused_cuda.split_planar(x), n, h, w, c)
+
+    def to_nhwc(self):
+        return load_ext().fused_cuda.merge_planar(self.data, self.n, self.h, self.w, self.c)
+
+
+def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=False):
+    """x1 [, x2]: Planar inputs (concatenated along channels); residual: Planar or None.
+    Returns a Planar, or an fp32 (N, H, W, Cout) tensor when nhwc_out."""
+    out = load_ext().fused_cuda.tc_conv3x3(x1.data, x1.c, None if x2 is None else x2.data, 0 if x2 is None else x2.c,
+                                           x1.n, x1.h, x1.w, packed, bias, None if residual is None else residual.data, relu, nhwc_out)
+    return out if nhwc_out else Planar(out, x1.n, x1.h, x1.w, bias.numel())
 
 
 def _nhwc(t):
-    """channels-last NCHW tensor -> its NHWC view (no copy when the memory format already is channels-last)."""
+    """logical NCHW tensor -> contiguous NHWC (no copy when the memory format already is channels-last)."""
     return t.permute(0, 2, 3, 1).contiguous()
 
 
@@ -95,33 +116,32 @@ class FastUNetResNet34:
         for up, fuse in ((net.deconv4, net.decoder3), (net.deconv3, net.decoder2), (net.deconv2, net.decoder1), (net.deconv1, net.decoder0)):
             wu, bu = fold_conv_bn(up[0], up[1])
             self.dec.append({'up_w': wu.float().contiguous(memory_format=cl), 'up_b': bu.float().contiguous(),
-                             'up_c': up[0].out_channels, 'fuse': mine(fuse[0], fuse[1])})
+                             'fuse': mine(fuse[0], fuse[1])})
 
     @torch.no_grad()
     def features_nhwc(self, x):
-        """image (n,3,h,w) fp32 -> 64-channel feature map (n, h, w, 64), a view of the (padded) NHWC output."""
+        """image (n,3,h,w) fp32 -> 64-channel feature map (n, h, w, 64) fp32, a view of the (padded) NHWC output."""
         h, w = x.shape[2], x.shape[3]
         pad_h, pad_w = (-h) % 16, (-w) % 16
         if pad_h or pad_w:
             x = F.pad(x, [0, pad_w, 0, pad_h])
         x = x.contiguous(memory_format=torch.channels_last)
         x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], self.stem_stride, self.stem_pad))
-        skips = [_nhwc(x)]
-        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
-        x = _nhwc(x)
+        skips = [Planar.from_nhwc(_nhwc(x))]
+        x = Planar.from_nhwc(_nhwc(F.max_pool2d(x, kernel_size=3, stride=2, padding=1)))
         for li, blocks in enumerate(self.layers):
             for e in blocks:
                 identity = x
                 if e['stride'] == 1:
-                    y = conv3x3_nhwc(x, *e['conv1'], relu=True)
-                else:
-                    y = _nhwc(F.relu_(F.conv2d(_nchw_view(x), e['conv1'][0], e['conv1'][1], e['stride'], 1)))
-                if e['down'] is not None:
-                    identity = _nhwc(F.conv2d(_nchw_view(x), e['down'][0], e['down'][1], e['down_stride'], 0))
-                x = conv3x3_nhwc(y, *e['conv2'], residual=identity, relu=True)
+                    y = conv3x3(x, *e['conv1'], relu=True)
+                else:                      # strided block: cuDNN on the merged fp32 view, results split again
+                    xf = _nchw_view(x.to_nhwc())
+                    y = Planar.from_nhwc(_nhwc(F.relu_(F.conv2d(xf, e['conv1'][0], e['conv1'][1], e['stride'], 1))))
+                    identity = Planar.from_nhwc(_nhwc(F.conv2d(xf, e['down'][0], e['down'][1], e['down_stride'], 0)))
+                x = conv3x3(y, *e['conv2'], residual=identity, relu=True)
             if li < 3:
                 skips.append(x)
-        for d, skip in zip(self.dec, (skips[3], skips[2], skips[1], skips[0])):
-            up = _nhwc(F.relu_(F.conv_transpose2d(_nchw_view(x), d['up_w'], d['up_b'], stride=2)))
-            x = conv3x3_nhwc(up, *d['fuse'], x2=skip, relu=True)
+        for i, (d, skip) in enumerate(zip(self.dec, (skips[3], skips[2], skips[1], skips[0]))):
+            up = F.relu_(F.conv_transpose2d(_nchw_view(x.to_nhwc()), d['up_w'], d['up_b'], stride=2))
+            x = conv3x3(Planar.from_nhwc(_nhwc(up)), *d['fuse'], x2=skip, relu=True, nhwc_out=(i == 3))
         return x[:, :h, :w, :]

@@ -40,18 +40,27 @@ def test_conv3x3_matches_float64(n, h, w, c1, c2, cout, res, relu):
     b = torch.randn(cout, device=dev)
     r = torch.randn(n, h, w, cout, device=dev) if res else None
     packed, bias = net2d.pack_conv3x3(wt, b)
-    got = net2d.conv3x3_nhwc(x1, packed, bias, x2=x2, residual=r, relu=relu)
+    P = net2d.Planar.from_nhwc
     want = ref_conv(x1, x2, wt, b, r, relu)
-    err = (got.double() - want).abs().max().item() / want.abs().max().item()
+    scale = want.abs().max().item()
+    # the split-planar round trip itself: hi + lo carries ~17 mantissa bits
+    assert (P(x1).to_nhwc() - x1).abs().max().item() <= 2 ** -16 * x1.abs().max().item()
+    got_p = net2d.conv3x3(P(x1), packed, bias, x2=None if x2 is None else P(x2), residual=None if r is None else P(r), relu=relu)
+    assert (got_p.n, got_p.h, got_p.w, got_p.c) == (n, h, w, cout)
+    err = (got_p.to_nhwc().double() - want).abs().max().item() / scale
+    assert err < 2e-5, err
+    got_f = net2d.conv3x3(P(x1), packed, bias, x2=None if x2 is None else P(x2), residual=None if r is None else P(r), relu=relu,
+                          nhwc_out=True)
+    err = (got_f.double() - want).abs().max().item() / scale
     assert err < 2e-5, err
 
 
 def test_conv3x3_errors():
     from mvpnet_b200 import net2d
-    x = torch.randn(1, 8, 8, 24, device='cuda')
+    x = net2d.Planar.from_nhwc(torch.randn(1, 8, 8, 24, device='cuda'))
     packed, bias = net2d.pack_conv3x3(torch.randn(16, 32, 3, 3), torch.zeros(16))
     with pytest.raises(RuntimeError):
-        net2d.conv3x3_nhwc(x, packed.cuda(), bias.cuda())          # 24 channels: not a multiple of 16 / wrong weight size
+        net2d.conv3x3(x, packed.cuda(), bias.cuda())               # 24 channels: not a multiple of 16 / wrong weight size
 
 
 def test_fast_unet_matches_module():

@@ -47,9 +47,21 @@ def test_plan_matches_module_features(monkeypatch):
     net.eval()
 
     class _Fused:
+        """CPU stand-ins with the extension's signatures: a "planar" tensor is simply the flat fp32 NHWC data."""
         @staticmethod
-        def tc_conv3x3(x1, x2, packed, bias, residual, relu):
-            return emulated_conv(x1, x2, packed, bias, residual, relu)
+        def split_planar(x):
+            return x.reshape(-1).clone()
+
+        @staticmethod
+        def merge_planar(p, n, h, w, c):
+            return p.reshape(n, h, w, c).clone()
+
+        @staticmethod
+        def tc_conv3x3(x1, c1, x2, c2, n, h, w, packed, bias, residual, relu, nhwc_out):
+            cout = bias.numel()
+            y = emulated_conv(x1.reshape(n, h, w, c1), None if x2 is None else x2.reshape(n, h, w, c2), packed, bias,
+                              None if residual is None else residual.reshape(n, h, w, cout), relu)
+            return y if nhwc_out else y.reshape(-1)
 
     class _Ext:
         fused_cuda = _Fused
