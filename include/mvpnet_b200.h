@@ -235,6 +235,23 @@ int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64
 int mvp_split_planar(const float *nhwc, int64_t N, int64_t H, int64_t W, int64_t C, void *planar, mvp_stream_t stream);
 int mvp_merge_planar(const void *planar, int64_t N, int64_t H, int64_t W, int64_t C, float *nhwc, mvp_stream_t stream);
 
+/* ==== the other layers of the 2D network on the tensor cores (csrc/tc_convg.cu) =====================
+ * mvp_tc_conv_general: x split-planar (N, Hi, Wi, Cin) -> out split-planar (N, Ho, Wo, Cout).
+ *   mode 0  convolution with `ntaps` taps: out[n,y,x,:] = act(bias + sum_t W_t . x[n, y*stride + dy[t], x*stride + dx[t], :])
+ *           (zero outside the input); stride 1 or 2; the caller passes the output grid.  Covers ResNet-34's three
+ *           stride-2 3x3 convolutions and 1x1 stride-2 down-samples (torchvision BasicBlock; unet_resnet34.py:17-28)
+ *           and, with mvp_unfold_stem, the 7x7 stem as seven row taps.
+ *   mode 1  2x2 / stride-2 transposed convolution (unet_resnet34.py:31-60 deconv*): ntaps = 1, tap (0,0),
+ *           Ho = 2 Hi, Wo = 2 Wi; GEMM column (2*ky + kx) * Cout + co.
+ * Weights: [G/Nt][Cin/16][tap][hi|lo][2][Nt][8] bf16 with G = Cout (mode 0) or 4*Cout (mode 1), Nt = min(Cout, 256).
+ * mvp_unfold_stem: fp32 NCHW 3-channel image -> split-planar (N, H, W, 32): channel kx*3 + c = image[n, c, y, x+kx-3].
+ * mvp_maxpool3x3s2_planar: 3x3 / stride 2 / pad 1 max-pool, split-planar in and out ((H-1)/2+1 x (W-1)/2+1). */
+int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_t Hi, int64_t Wi, int mode, int stride, int ntaps,
+                        const int *dy, const int *dx, int64_t Ho, int64_t Wo, const void *w_packed, const float *bias,
+                        int64_t Cout, int relu, void *out_planar, mvp_stream_t stream);
+int mvp_unfold_stem(const float *image_nchw, int64_t N, int64_t H, int64_t W, void *planar32, mvp_stream_t stream);
+int mvp_maxpool3x3s2_planar(const void *x, int64_t N, int64_t H, int64_t W, int64_t C, void *out, mvp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,3 +11,4 @@
 #include "fused_mlp.cu"
 #include "tc_mlp.cu"
 #include "tc_conv.cu"
+#include "tc_convg.cu"

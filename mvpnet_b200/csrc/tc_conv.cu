@@ -107,13 +107,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
       : "memory");
 }
 
-// one lane of the (converged) warp; ptxas then knows the guarded tcgen05 / bulk-copy instructions have one issuer
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
-  return p != 0;
-}
-
 __device__ __forceinline__ void unpack8(const uint4 h, const uint4 l, float (&v)[8]) {   // hi + lo -> fp32
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll

@@ -1,0 +1,426 @@
+// General tap-staged convolution on tcgen05 for the layers of the 2D network that tc_conv.cu's halo-patch scheme does
+// not cover (unet_resnet34.py:9-125): the three stride-2 3x3 convolutions and their 1x1 stride-2 down-sample
+// branches (torchvision BasicBlock), the four 2x2 stride-2 transposed convolutions of the decoder (as four 1x1
+// convolutions, one per output parity, scattered by the epilogue) and the 7x7 stem (as seven row taps over a
+// horizontally unfolded input, see unfold_stem_kernel).  Same arithmetic as tc_conv.cu: split-planar bf16 hi/lo
+// activations, three kind::f16 MMAs per K-step into an fp32 TMEM accumulator.
+//
+//   rows (GEMM M)  16 x 8 pixel tiles of the OUTPUT grid (of the INPUT grid for a transposed convolution)
+//   K loop         for every channel chunk (KC = 16..64 channels) and every tap (dy, dx): ONE TMA box load per plane
+//                  fetches the 128 input pixels (y*s + dy, x*s + dx) x KC channels — the stride s is the tensor map's
+//                  element stride, zero padding its out-of-bounds fill — straight into the UMMA operand layout
+//   weights        one ring stage per (chunk, tap), shared by the TM tiles a CTA keeps in flight
+#include "common.cuh"
+
+namespace mvp {
+namespace tcc {
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+
+constexpr int G_MAX_TAPS = 9;
+constexpr int G_MAX_STAGES = 6;
+
+struct ConvGArgs {
+  CUtensorMap mh, ml;               // input planes
+  int Cin, N;
+  int Hi, Wi;                       // input grid
+  int Hr, Wr;                       // row grid (tiles): output grid, or input grid when shuffle
+  int Ho, Wo;                       // output grid
+  int stride;                       // input pixel = row pixel * stride + tap offset
+  int ntaps;
+  int tdy[G_MAX_TAPS], tdx[G_MAX_TAPS];
+  int in_pair;                      // input planes are pair-interleaved (Hi <= 8)
+  int shuffle;                      // transposed 2x2/s2: output block nb -> parity, out pixel = 2 * row pixel + parity
+  const unsigned char *wp;          // [nb][Cin/16][tap][hi|lo][2][Nt][8] bf16 (the layout of tc_conv.cu with `ntaps` taps)
+  const float *bias;                // [Cout]
+  __nv_bfloat16 *out_p;             // split-planar output (Ho x Wo, Cout channels)
+  long long plane_out;
+  int Cout, Nt, NB;                 // NB blocks of Nt GEMM columns (shuffle: 4 * Cout / Nt)
+  int relu;
+  int KC, nchunks;
+  int TX, TY;
+  long long ntiles, ngroups;
+  int TM, nacc, astages, stages, tmem_cols;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_half = (uint32_t)(a.KC >> 3) * 2048u;         // hi (or lo) of one tile's stage: KC/8 slabs x 128 rows x 16 B
+  const uint32_t a_tile = 2u * a_half;
+  const uint32_t a_stage = (uint32_t)a.TM * a_tile;
+  const uint32_t b_stage = (uint32_t)a.KC * (uint32_t)a.Nt * 4u;
+  unsigned char *a_base = smem;
+  unsigned char *b_base = a_base + (size_t)a.astages * a_stage;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)a.stages * b_stage);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * G_MAX_STAGES + 4);
+  const uint32_t bar_bfull = smem_u32(bars), bar_bempty = bar_bfull + 8 * G_MAX_STAGES;
+  const uint32_t bar_afull = bar_bempty + 8 * G_MAX_STAGES, bar_aempty = bar_afull + 8 * G_MAX_STAGES;
+  const uint32_t bar_accfull = bar_aempty + 8 * G_MAX_STAGES, bar_accempty = bar_accfull + 16;
+
+  if (tid == 0) {
+    for (int s = 0; s < G_MAX_STAGES; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1);
+      mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, EPI_THREADS); }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long nworks = a.ngroups * a.NB;
+  const uint32_t S = (uint32_t)a.stages, AS = (uint32_t)a.astages, NA = (uint32_t)a.nacc;
+  const int per_img = a.TX * a.TY;
+  const int iters = a.nchunks * a.ntaps;                         // K-loop length of one work item
+
+  if (warp < 4) {
+    // =========================== epilogue ============================================================================
+    const int row = warp * 32 + lane, g = row >> 3, xx = row & 7;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int C8o = a.Cout >> 3, out_pair = a.Ho <= 8;
+    const size_t slab_stride = (size_t)a.Ho * a.Wo * 8 * (out_pair ? 2 : 1);
+    const int blocks_per_parity = a.shuffle ? a.Cout / a.Nt : 0;
+    uint32_t it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++it) {
+      const int nb = (int)(w / a.ngroups);
+      const long long group = w - (long long)nb * a.ngroups;
+      const uint32_t set = it % NA;
+      int py = 0, px = 0, co0 = nb * a.Nt;
+      if (a.shuffle) { const int par = nb / blocks_per_parity; py = par >> 1; px = par & 1; co0 = (nb - par * blocks_per_parity) * a.Nt; }
+      mbar_wait(bar_accfull + 8 * set, (it / NA) & 1u);
+      tc_fence_after();
+      for (int t = 0; t < a.TM; ++t) {
+        const long long tile = group * a.TM + t;
+        if (tile >= a.ntiles) break;
+        const int n = (int)(tile / per_img), r = (int)(tile - (long long)n * per_img);
+        const int yr = (r / a.TX) * 16 + g, xr = (r % a.TX) * 8 + xx;
+        const bool ok = yr < a.Hr && xr < a.Wr;
+        const int yo = a.shuffle ? 2 * yr + py : yr, xo = a.shuffle ? 2 * xr + px : xr;
+        const size_t pbase = ok ? planar_off(n, co0 >> 3, yo, xo, C8o, a.Ho, a.Wo, out_pair) : 0;
+        const uint32_t t_acc = t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
+        uint32_t rn[16];
+        tmem_ld16_issue(t_acc, rn);
+        for (int c = 0; c < a.Nt; c += 16) {
+          float v[16];
+          tmem_ld_wait(rn);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
+          if (c + 16 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 16), rn);
+          const float4 *bp = reinterpret_cast<const float4 *>(a.bias + co0 + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bq = __ldg(bp + q);
+            v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          if (ok) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) split_pair(v[8 * s + 2 * q], v[8 * s + 2 * q + 1], h[q], l[q]);
+              const size_t o = pbase + (size_t)((c >> 3) + s) * slab_stride;
+              *reinterpret_cast<uint4 *>(a.out_p + o) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4 *>(a.out_p + a.plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_accempty + 8 * set);
+    }
+  } else if (warp == 4) {
+    // =========================== MMA issuer (whole warp walks, one elected lane issues) ==============================
+    const uint32_t idesc = make_idesc(128, a.Nt);
+    const uint32_t a_s = smem_u32(a_base), b_s = smem_u32(b_base);
+    const uint64_t adesc0 = make_desc(0, 2048, 128), bdesc0 = make_desc(0, (uint32_t)a.Nt * 16u, 128);
+    const uint32_t b_piece = 64u * (uint32_t)a.Nt, b_half = b_piece >> 1;   // one 16-channel piece: hi | lo
+    const int ksteps = a.KC >> 4;
+    uint32_t a_it = 0, w_it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++w_it) {
+      const long long group = w % a.ngroups;
+      const long long left = a.ntiles - group * a.TM;
+      const int nt = left < a.TM ? (int)left : a.TM;
+      const uint32_t set = w_it % NA;
+      if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, ((w_it / NA) - 1u) & 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + set * (uint32_t)(a.TM * a.Nt);
+      for (int i = 0; i < iters; ++i, ++a_it) {
+        const uint32_t sa = a_it % AS, sb = a_it % S;
+        mbar_wait(bar_afull + 8 * sa, (a_it / AS) & 1u);
+        mbar_wait(bar_bfull + 8 * sb, (a_it / S) & 1u);
+        const uint32_t a_st = a_s + sa * a_stage, b_hi = b_s + sb * b_stage;
+        if (elect_one()) {
+          for (int t = 0; t < nt; ++t) {
+            const uint32_t d = d0 + (uint32_t)(t * a.Nt);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t ah_a = a_st + (uint32_t)t * a_tile + (uint32_t)k * 4096u, bh_a = b_hi + (uint32_t)k * b_piece;
+              const uint64_t ah = adesc0 | (uint64_t)((ah_a >> 4) & 0x3fffu), al = adesc0 | (uint64_t)(((ah_a + a_half) >> 4) & 0x3fffu);
+              const uint64_t bh = bdesc0 | (uint64_t)((bh_a >> 4) & 0x3fffu), bl = bdesc0 | (uint64_t)(((bh_a + b_half) >> 4) & 0x3fffu);
+              umma_bf16(d, ah, bh, idesc, (i == 0 && k == 0) ? 0u : 1u);
+              umma_bf16(d, ah, bl, idesc, 1u);
+              umma_bf16(d, al, bh, idesc, 1u);
+            }
+          }
+          umma_commit(bar_bempty + 8 * sb);
+          umma_commit(bar_aempty + 8 * sa);
+          if (i == iters - 1) umma_commit(bar_accfull + 8 * set);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 5) {
+    // =========================== input producer: one TMA box per (tile, chunk, tap, plane) ===========================
+    const uint32_t a_s = smem_u32(a_base);
+    const int C8 = a.Cin >> 3, kslabs = a.KC >> 3;
+    uint32_t it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
+      const long long group = w % a.ngroups;
+      const long long left = a.ntiles - group * a.TM;
+      const int nt = left < a.TM ? (int)left : a.TM;
+      for (int c = 0; c < a.nchunks; ++c) {
+        for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
+          const uint32_t sa = it % AS;
+          if (it >= AS) mbar_wait(bar_aempty + 8 * sa, ((it / AS) - 1u) & 1u);
+          if (elect_one()) {
+            mbar_expect_tx(bar_afull + 8 * sa, (uint32_t)nt * a_tile);
+            for (int t = 0; t < nt; ++t) {
+              const long long tile = group * a.TM + t;
+              const int n = (int)(tile / per_img), r = (int)(tile - (long long)n * per_img);
+              const int y = (r / a.TX) * 16 * a.stride + a.tdy[tap], x = (r % a.TX) * 8 * a.stride + a.tdx[tap];
+              const uint32_t dst = a_s + sa * a_stage + (uint32_t)t * a_tile;
+              if (!a.in_pair) {            // dims (8, W, H, C8 * N)
+                tma_load_4d(dst, &a.mh, 0, x, y, n * C8 + c * kslabs, bar_afull + 8 * sa);
+                tma_load_4d(dst + a_half, &a.ml, 0, x, y, n * C8 + c * kslabs, bar_afull + 8 * sa);
+              } else {                     // dims (8, W, 2, H, C8 * N/2)
+                tma_load_5d(dst, &a.mh, 0, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar_afull + 8 * sa);
+                tma_load_5d(dst + a_half, &a.ml, 0, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar_afull + 8 * sa);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =========================== weight producer: KC/16 pieces per stage ============================================
+    const uint32_t b_s = smem_u32(b_base);
+    const uint32_t b_piece = 64u * (uint32_t)a.Nt;
+    const int ks = a.KC >> 4, nch16 = a.Cin >> 4;
+    uint32_t it = 0;
+    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
+      const int nb = (int)(w / a.ngroups);
+      const unsigned char *wsrc = a.wp + (size_t)nb * nch16 * a.ntaps * b_piece;
+      for (int c = 0; c < a.nchunks; ++c) {
+        for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
+          const uint32_t s = it % S;
+          if (it >= S) mbar_wait(bar_bempty + 8 * s, ((it / S) - 1u) & 1u);
+          if (elect_one()) {
+            mbar_expect_tx(bar_bfull + 8 * s, b_stage);
+            for (int k = 0; k < ks; ++k)
+              bulk_g2s(b_s + s * b_stage + (uint32_t)k * b_piece, wsrc + ((size_t)(c * ks + k) * a.ntaps + tap) * b_piece, b_piece, bar_bfull + 8 * s);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// ---- stem helper: fp32 NCHW image (3 channels) -> split-planar "row-unfolded" tensor with 32 channels per pixel:
+// channel kx*3 + c = image[n, c, y, x + kx - 3] (zero outside), channels 21..31 zero.  The 7x7 convolution is then
+// seven row taps (dy = -3..3, dx = 0) over this tensor (unet_resnet34.py:16-21 encoder0).
+__global__ void __launch_bounds__(256)
+unfold_stem_kernel(const float *__restrict__ img, int N, int H, int W, __nv_bfloat16 *__restrict__ dst, long long plane) {
+  const long long total = (long long)N * 4 * H * W;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int x = (int)(i % W);
+    long long r = i / W;
+    const int y = (int)(r % H); r /= H;
+    const int c8 = (int)(r % 4);
+    const int n = (int)(r / 4);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = c8 * 8 + e, kx = ch / 3, c = ch - kx * 3, xs = x + kx - 3;
+      v[e] = (ch < 21 && xs >= 0 && xs < W) ? __ldg(img + (((size_t)n * 3 + c) * H + y) * W + xs) : 0.f;
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
+    const size_t o = planar_off(n, c8, y, x, 4, H, W, 0);
+    *reinterpret_cast<uint4 *>(dst + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(dst + plane + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// ---- 3x3 / stride 2 / pad 1 max-pool on split-planar tensors (unet_resnet34.py:88 maxpool): thread = (n, slab, yo, xo)
+__global__ void __launch_bounds__(256)
+maxpool_planar_kernel(const __nv_bfloat16 *__restrict__ src, long long plane_in, int N, int H, int W, int C, int Ho, int Wo,
+                      __nv_bfloat16 *__restrict__ dst, long long plane_out) {
+  const int C8 = C >> 3, in_pair = H <= 8, out_pair = Ho <= 8;
+  const long long total = (long long)N * C8 * Ho * Wo;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xo = (int)(i % Wo);
+    long long r = i / Wo;
+    const int yo = (int)(r % Ho); r /= Ho;
+    const int c8 = (int)(r % C8);
+    const int n = (int)(r / C8);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -__int_as_float(0x7f800000);
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * yo + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * xo + dx;
+        if (x < 0 || x >= W) continue;
+        const size_t o = planar_off(n, c8, y, x, C8, H, W, in_pair);
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4 *>(src + o)), __ldg(reinterpret_cast<const uint4 *>(src + plane_in + o)), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_pair(m[2 * q], m[2 * q + 1], h[q], l[q]);
+    const size_t o = planar_off(n, c8, yo, xo, C8, Ho, Wo, out_pair);
+    *reinterpret_cast<uint4 *>(dst + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(dst + plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// tensor map over one plane with unmerged (channel-in-slab, x, [pair,] y, slab) dimensions and a traversal stride
+static int make_plane_map_g(CUtensorMap *m, const void *plane, int64_t N, int64_t H, int64_t W, int64_t C, int pair, int stride, int kslabs) {
+  EncodeTiledFn enc = encode_tiled();
+  MVP_REQUIRE(enc != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv: cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t C8 = (cuuint64_t)(C / 8);
+  const cuuint32_t st = (cuuint32_t)stride;
+  CUresult r;
+  if (!pair) {
+    const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, C8 * (cuuint64_t)N};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+    const cuuint32_t box[4] = {8, 8 * st, 16 * st, (cuuint32_t)kslabs}, es[4] = {1, st, st, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W, 2, (cuuint64_t)H, C8 * (cuuint64_t)((N + 1) / 2)};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)2 * W * 16, (cuuint64_t)H * 2 * W * 16};
+    const cuuint32_t box[5] = {8, 8 * st, 1, 16 * st, (cuuint32_t)kslabs}, es[5] = {1, st, 1, st, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  MVP_REQUIRE(r == CUDA_SUCCESS, MVP_ERR_INVALID_ARG, "tc_conv: cuTensorMapEncodeTiled failed (%d) for N=%lld H=%lld W=%lld C=%lld stride=%d", (int)r,
+              (long long)N, (long long)H, (long long)W, (long long)C, stride);
+  return 0;
+}
+
+}  // namespace tcc
+}  // namespace mvp
+
+// mode 0: convolution with `ntaps` taps (dy[i], dx[i]) and stride `stride` (output grid Ho x Wo given by the caller);
+// mode 1: 2x2 / stride-2 transposed convolution (ntaps must be 1, tap (0,0); GEMM columns = 4 parities x Cout)
+extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_t Hi, int64_t Wi, int mode, int stride, int ntaps,
+                                   const int *dy, const int *dx, int64_t Ho, int64_t Wo, const void *w_packed, const float *bias,
+                                   int64_t Cout, int relu, void *out_planar, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(N >= 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, MVP_ERR_INVALID_ARG, "tc_conv_general: bad sizes");
+  MVP_REQUIRE(Cin > 0 && Cin % 16 == 0 && Cout > 0 && Cout % 16 == 0 && (Cout <= 256 || Cout % 256 == 0), MVP_ERR_UNSUPPORTED,
+              "tc_conv_general: channels must be multiples of 16 (Cout a multiple of 256 above 256)");
+  MVP_REQUIRE((mode == 0 || mode == 1) && (stride == 1 || stride == 2) && ntaps >= 1 && ntaps <= tcc::G_MAX_TAPS && dy && dx, MVP_ERR_INVALID_ARG,
+              "tc_conv_general: bad mode / stride / taps");
+  MVP_REQUIRE(mode == 0 || (ntaps == 1 && stride == 1 && Ho == 2 * Hi && Wo == 2 * Wi), MVP_ERR_INVALID_ARG,
+              "tc_conv_general: a transposed convolution has one tap and doubles the grid");
+  MVP_REQUIRE(N * Ho * Wo < (1LL << 31) && N * Hi * Wi < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv_general: more than 2^31 pixels");
+  if (N == 0) return 0;
+  MVP_REQUIRE(x && w_packed && bias && out_planar, MVP_ERR_NULL, "tc_conv_general: null pointer");
+  tcc::ConvGArgs a = {};
+  a.Cin = (int)Cin; a.N = (int)N; a.Hi = (int)Hi; a.Wi = (int)Wi; a.Ho = (int)Ho; a.Wo = (int)Wo;
+  a.shuffle = mode; a.stride = stride; a.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) { a.tdy[i] = dy[i]; a.tdx[i] = dx[i]; }
+  a.Hr = mode ? (int)Hi : (int)Ho; a.Wr = mode ? (int)Wi : (int)Wo;
+  a.in_pair = Hi <= 8 ? 1 : 0;
+  const int64_t Np_in = a.in_pair ? (N + 1) / 2 * 2 : N, Np_out = Ho <= 8 ? (N + 1) / 2 * 2 : N;
+  a.wp = (const unsigned char *)w_packed; a.bias = bias; a.out_p = (__nv_bfloat16 *)out_planar; a.plane_out = Np_out * Cout * Ho * Wo;
+  a.relu = relu; a.Cout = (int)Cout; a.Nt = Cout <= 256 ? (int)Cout : 256;
+  a.NB = (mode ? 4 : 1) * (a.Cout / a.Nt);
+  a.TX = (a.Wr + 7) / 8; a.TY = (a.Hr + 15) / 16;
+  a.ntiles = N * a.TX * a.TY;
+  a.TM = a.Nt <= 64 ? 4 : 2;
+  while (a.TM > 1 && (a.ntiles + a.TM - 1) / a.TM * a.NB < sm_count()) a.TM >>= 1;
+  a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
+  a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
+  // channels per stage: a stage holds TM tiles x KC channels x 512 B (hi + lo), kept at <= 32 KB
+  a.KC = 64 / a.TM;
+  while (a.KC > 16 && Cin % a.KC != 0) a.KC >>= 1;
+  a.nchunks = (int)(Cin / a.KC);
+  if (int rc = tcc::make_plane_map_g(&a.mh, x, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
+  if (int rc = tcc::make_plane_map_g(&a.ml, (const __nv_bfloat16 *)x + Np_in * Cin * Hi * Wi, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
+  const size_t a_stage = (size_t)a.TM * a.KC * 512, b_stage = (size_t)a.KC * a.Nt * 4;
+  a.astages = a.stages = tcc::G_MAX_STAGES;
+  auto smem_of = [&]() { return a.astages * a_stage + a.stages * b_stage + 512; };
+  while (smem_of() > tc::SMEM_CAP && (a.astages > 2 || a.stages > 2)) {
+    if (a.astages >= a.stages && a.astages > 2) --a.astages; else if (a.stages > 2) --a.stages; else --a.astages;
+  }
+  const size_t smem = smem_of();
+  MVP_REQUIRE(smem <= tc::SMEM_CAP, MVP_ERR_UNSUPPORTED, "tc_conv_general: shared memory budget exceeded");
+  cudaError_t e = cudaFuncSetAttribute(tcc::tc_convg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("tc_conv_general: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
+  const long long nworks = a.ngroups * a.NB;
+  long long grid = sm_count();
+  if (grid > nworks) grid = nworks;
+  static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
+  if (debug)
+    fprintf(stderr, "[tc_conv_general] N=%d in=%dx%d out=%dx%d Cin=%d Cout=%d mode=%d stride=%d taps=%d Nt=%d NB=%d KC=%d tiles=%lld TM=%d nacc=%d works=%lld astages=%d stages=%d smem=%zu\n",
+            a.N, a.Hi, a.Wi, a.Ho, a.Wo, a.Cin, a.Cout, mode, stride, ntaps, a.Nt, a.NB, a.KC, a.ntiles, a.TM, a.nacc, nworks, a.astages, a.stages, smem);
+  tcc::tc_convg_kernel<<<(unsigned)grid, tcc::THREADS, smem, (cudaStream_t)stream>>>(a);
+  return launch_status("tc_conv_general");
+}
+
+extern "C" int mvp_unfold_stem(const float *image_nchw, int64_t N, int64_t H, int64_t W, void *planar32, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(N >= 0 && H > 8 && W > 0, MVP_ERR_INVALID_ARG, "unfold_stem: bad sizes (H must exceed 8)");
+  if (N == 0) return 0;
+  MVP_REQUIRE(image_nchw && planar32, MVP_ERR_NULL, "unfold_stem: null pointer");
+  const long long total = N * 4 * H * W;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
+  tcc::unfold_stem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image_nchw, (int)N, (int)H, (int)W, (__nv_bfloat16 *)planar32, N * 32 * H * W);
+  return launch_status("unfold_stem");
+}
+
+extern "C" int mvp_maxpool3x3s2_planar(const void *x, int64_t N, int64_t H, int64_t W, int64_t C, void *out, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(N >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, MVP_ERR_INVALID_ARG, "maxpool_planar: bad sizes");
+  if (N == 0) return 0;
+  MVP_REQUIRE(x && out, MVP_ERR_NULL, "maxpool_planar: null pointer");
+  const int64_t Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t Np_in = H <= 8 ? (N + 1) / 2 * 2 : N, Np_out = Ho <= 8 ? (N + 1) / 2 * 2 : N;
+  if (Np_out != N) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)Np_out * C * Ho * Wo * 4, (cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("maxpool_planar: memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  const long long total = N * (C / 8) * Ho * Wo;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
+  tcc::maxpool_planar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, Np_in * C * H * W, (int)N, (int)H, (int)W, (int)C,
+                                                                    (int)Ho, (int)Wo, (__nv_bfloat16 *)out, Np_out * C * Ho * Wo);
+  return launch_status("maxpool_planar");
+}

@@ -98,6 +98,12 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// one lane of the (converged) warp; ptxas then knows the guarded tcgen05 / bulk-copy instructions have one issuer
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void group_sync(int g) {   // the 256 workers of tile group g (barrier 0 is __syncthreads)
   asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GROUP_THREADS) : "memory");
 }
@@ -544,25 +550,29 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
       }
     }
   } else if (warp == NW) {
-    // =========================== MMA issuer (one elected lane) ======================================================
-    if (lane == 0) {
-      uint32_t ph[MAX_GROUPS] = {0u, 0u, 0u};
-      uint32_t q_cons = 0;
-      for (long long r = 0; r < rounds; ++r) {
-        for (int sg = 0; sg < nsegs; ++sg) {
-          int l, kbeg, klen;
-          seg_info(sg, l, kbeg, klen);
-          const int K = m.k[l], N = m.n[l];
+    // =========================== MMA issuer ==========================================================================
+    // The whole warp walks the request order (all values warp-uniform -> descriptors in uniform registers) and one
+    // elected lane issues: under `if (lane == 0)` ptxas wraps every tcgen05 instruction in a thread-by-thread
+    // broadcast loop that costs more than a narrow layer's MMA takes to execute.
+    uint32_t ph[MAX_GROUPS] = {0u, 0u, 0u};
+    uint32_t q_cons = 0;
+    const uint32_t smem_s = smem_u32(smem), wreg_s = smem_u32(wreg);
+    for (long long r = 0; r < rounds; ++r) {
+      for (int sg = 0; sg < nsegs; ++sg) {
+        int l, kbeg, klen;
+        seg_info(sg, l, kbeg, klen);
+        const int K = m.k[l], N = m.n[l];
 #pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (r * NG + g >= n_my) continue;
-            mbar_wait(bar_aready0 + 8 * g, ph[g]);
-            ph[g] ^= 1u;
-            tc_fence_after();
-            const uint32_t a_hi_s = smem_u32(smem + (size_t)g * 2 * a_bytes), a_lo_s = a_hi_s + (uint32_t)a_bytes;
-            const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
-            if (m.resident) {
-              const uint32_t wbase = smem_u32(wreg + m.res_off[l]);
+        for (int g = 0; g < NG; ++g) {
+          if (r * NG + g >= n_my) continue;
+          mbar_wait(bar_aready0 + 8 * g, ph[g]);
+          ph[g] ^= 1u;
+          tc_fence_after();
+          const uint32_t a_hi_s = smem_s + (uint32_t)((size_t)g * 2 * a_bytes), a_lo_s = a_hi_s + (uint32_t)a_bytes;
+          const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
+          if (m.resident) {
+            const uint32_t wbase = wreg_s + (uint32_t)m.res_off[l];
+            if (elect_one()) {
               for (int n0 = 0; n0 < N; n0 += 256) {
                 const uint32_t nb = (uint32_t)min(256, N - n0);
                 const uint32_t idesc = make_idesc(ROWS, (int)nb);
@@ -573,62 +583,66 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
                               idesc, k0 == 0);
                 }
               }
-            } else {
-              const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
-              for (int c = 0; c < total; ++c) {
-                const uint32_t s = q_cons % S;
-                const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
-                const uint32_t nb = (uint32_t)min(256, N - n0);
-                const int kc = min(m.kc, kbeg + klen - k0);
-                const uint32_t idesc = make_idesc(ROWS, (int)nb);
-                mbar_wait(bar_full0 + 8 * s, (q_cons / S) & 1u);                       // the chunk has landed
-                tc_fence_after();
-                const uint32_t wh = smem_u32(wreg + (size_t)s * 2 * stage_half), wl = wh + (uint32_t)stage_half;
+              umma_commit(bar_acc0 + 8 * g);
+            }
+            __syncwarp();
+          } else {
+            const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
+            for (int c = 0; c < total; ++c) {
+              const uint32_t s = q_cons % S;
+              const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+              const uint32_t nb = (uint32_t)min(256, N - n0);
+              const int kc = min(m.kc, kbeg + klen - k0);
+              const uint32_t idesc = make_idesc(ROWS, (int)nb);
+              mbar_wait(bar_full0 + 8 * s, (q_cons / S) & 1u);                       // the chunk has landed
+              const uint32_t wh = wreg_s + s * (uint32_t)(2 * stage_half), wl = wh + (uint32_t)stage_half;
+              if (elect_one()) {
                 for (int j = 0; j < kc; j += 16) {
                   const uint32_t ka = (uint32_t)((k0 + j - kbeg) >> 3), js = (uint32_t)(j >> 3);
                   issue_kstep(t_group + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + js * nb * 16, wl + js * nb * 16, nb,
                               idesc, k0 + j == 0);
                 }
-                umma_commit(bar_empty0 + 8 * s);                                       // frees the stage when these MMAs retire
-                ++q_cons;
+                umma_commit(bar_empty0 + 8 * s);                                     // frees the stage when these MMAs retire
+                if (c == total - 1) umma_commit(bar_acc0 + 8 * g);
               }
+              __syncwarp();
+              ++q_cons;
             }
-            umma_commit(bar_acc0 + 8 * g);
           }
         }
       }
     }
-    __syncwarp();
   } else if (!m.resident) {
-    // =========================== weight producer (one elected lane): same request order, runs ahead =================
-    if (lane == 0) {
-      uint32_t q_prod = 0;
-      for (long long r = 0; r < rounds; ++r) {
-        for (int sg = 0; sg < nsegs; ++sg) {
-          int l, kbeg, klen;
-          seg_info(sg, l, kbeg, klen);
-          const int K = m.k[l], N = m.n[l];
-          const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
-          for (int g = 0; g < NG; ++g) {
-            if (r * NG + g >= n_my) continue;
-            for (int c = 0; c < total; ++c) {
-              const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
-              const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kbeg + klen - k0);
-              const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
-              if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);  // MMAs of the previous use have retired
-              const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
-              const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
-              const uint32_t dst = smem_u32(wreg + (size_t)s * 2 * stage_half);
+    // =========================== weight producer: same request order, runs ahead ======================================
+    uint32_t q_prod = 0;
+    const uint32_t wreg_s = smem_u32(wreg);
+    for (long long r = 0; r < rounds; ++r) {
+      for (int sg = 0; sg < nsegs; ++sg) {
+        int l, kbeg, klen;
+        seg_info(sg, l, kbeg, klen);
+        const int K = m.k[l], N = m.n[l];
+        const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
+        for (int g = 0; g < NG; ++g) {
+          if (r * NG + g >= n_my) continue;
+          for (int c = 0; c < total; ++c) {
+            const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+            const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kbeg + klen - k0);
+            const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
+            if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);  // MMAs of the previous use have retired
+            const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+            const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+            const uint32_t dst = wreg_s + s * (uint32_t)(2 * stage_half);
+            if (elect_one()) {
               mbar_expect_tx(bar_full0 + 8 * s, 2 * bytes);
               bulk_g2s(dst, gh, bytes, bar_full0 + 8 * s);
               bulk_g2s(dst + (uint32_t)stage_half, gl, bytes, bar_full0 + 8 * s);
-              ++q_prod;
             }
+            __syncwarp();
+            ++q_prod;
           }
         }
       }
     }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

@@ -457,6 +457,48 @@ at::Tensor tc_conv3x3(const at::Tensor x1, int64_t C1, const c10::optional<at::T
   return out;
 }
 
+at::Tensor planar_empty(const at::Tensor &like, int64_t N, int64_t H, int64_t W, int64_t C) {
+  // an odd image count leaves a partner-less image in the last pair of a pair-interleaved tensor: keep it zero
+  auto opt = like.options().dtype(at::kBFloat16);
+  return (H <= 8 && (N & 1)) ? at::zeros({mvp_planar_elems(N, H, W, C)}, opt) : at::empty({mvp_planar_elems(N, H, W, C)}, opt);
+}
+
+// mode 0: taps (dy, dx) convolution with stride; mode 1: 2x2 / stride-2 transposed convolution
+at::Tensor tc_conv_general(const at::Tensor x, int64_t Cin, int64_t N, int64_t Hi, int64_t Wi, int64_t mode, int64_t stride,
+                           const std::vector<int64_t> dy, const std::vector<int64_t> dx, int64_t Ho, int64_t Wo, const at::Tensor w_packed,
+                           const at::Tensor bias, bool relu) {
+  CHECK_INPUT(x); CHECK_INPUT(w_packed); CHECK_INPUT(bias); CHECK_F32(bias);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.numel() == mvp_planar_elems(N, Hi, Wi, Cin), "tc_conv_general: x is not split-planar (N,Hi,Wi,Cin)");
+  TORCH_CHECK(dy.size() == dx.size() && !dy.empty() && dy.size() <= 9, "tc_conv_general: 1..9 taps");
+  const auto Cout = bias.size(0);
+  const int64_t G = mode ? 4 * Cout : Cout;
+  TORCH_CHECK(w_packed.numel() * w_packed.element_size() == (int64_t)dy.size() * Cin * G * 4, "tc_conv_general: packed weights have the wrong size");
+  std::vector<int> idy(dy.begin(), dy.end()), idx(dx.begin(), dx.end());
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = planar_empty(x, N, Ho, Wo, Cout);
+  check_rc(mvp_tc_conv_general(x.data_ptr(), Cin, N, Hi, Wi, (int)mode, (int)stride, (int)dy.size(), idy.data(), idx.data(), Ho, Wo,
+                               w_packed.data_ptr(), bias.data_ptr<float>(), Cout, relu ? 1 : 0, out.data_ptr(), cur_stream()));
+  return out;
+}
+
+at::Tensor unfold_stem(const at::Tensor image) {
+  CHECK_INPUT(image); CHECK_F32(image);
+  TORCH_CHECK(image.dim() == 4 && image.size(1) == 3, "unfold_stem: image must be fp32 (N, 3, H, W)");
+  c10::cuda::CUDAGuard guard(image.device());
+  auto out = at::empty({mvp_planar_elems(image.size(0), image.size(2), image.size(3), 32)}, image.options().dtype(at::kBFloat16));
+  check_rc(mvp_unfold_stem(image.data_ptr<float>(), image.size(0), image.size(2), image.size(3), out.data_ptr(), cur_stream()));
+  return out;
+}
+
+at::Tensor maxpool3x3s2_planar(const at::Tensor x, int64_t N, int64_t H, int64_t W, int64_t C) {
+  CHECK_INPUT(x);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && x.numel() == mvp_planar_elems(N, H, W, C), "maxpool_planar: x is not split-planar (N,H,W,C)");
+  c10::cuda::CUDAGuard guard(x.device());
+  auto out = at::empty({mvp_planar_elems(N, (H - 1) / 2 + 1, (W - 1) / 2 + 1, C)}, x.options());
+  check_rc(mvp_maxpool3x3s2_planar(x.data_ptr(), N, H, W, C, out.data_ptr(), cur_stream()));
+  return out;
+}
+
 bool tc_chain_supported(const std::vector<int64_t> ks, const std::vector<int64_t> ns, int64_t mode) {
   mvp_tc_chain_t c = {};
   if (ks.empty() || ks.size() > MVP_MLP_MAX_LAYERS || ks.size() != ns.size()) return false;
@@ -582,6 +624,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
   fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
   fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv on split-planar activations, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
+  fz.def("tc_conv_general", &tc_conv_general, "tap-staged conv / 2x2 transposed conv on split-planar activations (tcgen05)");
+  fz.def("unfold_stem", &unfold_stem, "fp32 NCHW image -> row-unfolded split-planar (32 channels) for the 7x7 stem");
+  fz.def("maxpool3x3s2_planar", &maxpool3x3s2_planar, "3x3/s2/p1 max-pool on split-planar activations");
   fz.def("split_planar", &split_planar, "fp32 NHWC -> split-planar bf16 hi/lo");
   fz.def("merge_planar", &merge_planar, "split-planar bf16 hi/lo -> fp32 NHWC");
   fz.def("tc_feature_aggregation", &tc_feature_aggregation, "pixel gather + relation + MLP (tcgen05) + sum/max");

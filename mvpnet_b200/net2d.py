@@ -1,14 +1,14 @@
 """The 2D network of MVPNet3D.forward (mvpnet_3d.py:94-99; architecture unet_resnet34.py:9-125) on this package's
 tensor-core convolution (csrc/tc_conv.cu) for inference.
 
-Activations are fp32 NHWC end to end.  Every 3x3 / stride-1 convolution (92 % of the network's multiply-adds: all of
-ResNet-34's residual-block convolutions except the three strided ones, and the four decoder convolutions, whose
-cat([up, skip]) input is read from the two tensors in place) runs as an implicit GEMM on tcgen05 with a bf16 hi/lo
-split x 3 products (fp32-level accuracy, see tc_mlp.cu); eval BatchNorm is folded into weights and bias, ReLU and the
-residual add ride in the epilogue.  The remaining layers (7x7 stem, max-pool, three stride-2 3x3, three 1x1
-down-samples, four 2x2 transposed convolutions) stay on cuDNN / ATen in channels-last fp32 so that no layout
-conversion happens anywhere.  The final 64-channel feature map is returned NHWC, which is exactly the layout the
-fused FeatureAggregation gather wants (one 256-byte row per pixel).
+Activations are "split-planar" (bf16 hi + bf16 lo planes of 8-channel slabs, include/mvpnet_b200.h) from the stem to
+the last decoder layer.  Every 3x3 / stride-1 convolution (92 % of the network's multiply-adds: ResNet-34's
+residual-block convolutions and the four decoder convolutions, whose cat([up, skip]) input is read from the two
+tensors in place) runs on csrc/tc_conv.cu; the three stride-2 3x3 convolutions, the 1x1 down-samples, the 2x2
+transposed convolutions and the 7x7 stem run on csrc/tc_convg.cu; all as implicit GEMMs on tcgen05 with a bf16
+hi/lo split x 3 products (fp32-level accuracy, see tc_mlp.cu).  Eval BatchNorm is folded into weights and bias; ReLU
+and the residual add ride in the epilogues.  No cuDNN call and no layout conversion is left.  The final 64-channel
+feature map is written fp32 NHWC, the layout the fused FeatureAggregation gather wants (one 256-byte row per pixel).
 """
 import torch
 from torch import nn
@@ -32,20 +32,58 @@ def fold_conv_bn(conv, bn):
     return w, b
 
 
-def pack_conv3x3(weight, bias):
-    """weight (Cout, Cin, 3, 3), bias (Cout) (any float dtype) -> (packed uint8 tensor, fp32 bias) in the operand order
-    of mvp_tc_conv3x3: [Cout/Nt][Cin/16][tap][hi|lo][2][Nt][8] bf16."""
-    cout, cin = weight.shape[0], weight.shape[1]
-    assert weight.shape[2:] == (3, 3) and cin % 16 == 0 and cout % 16 == 0
-    nt = cout if cout <= 256 else 256
-    assert cout % nt == 0
-    w = weight.float()
+def pack_taps(wg, nt):
+    """wg (G, Cin, T) (any float dtype), G % nt == 0, Cin % 16 == 0 -> uint8 tensor in the operand order of the
+    tensor-core convolutions: [G/nt][Cin/16][T][hi|lo][2][nt][8] bf16."""
+    g, cin, t = wg.shape
+    assert g % nt == 0 and cin % 16 == 0
+    w = wg.float()
     hi = w.bfloat16()
     lo = (w - hi.float()).bfloat16()
-    x = torch.stack([hi, lo])                                             # (hl, Cout, Cin, ky, kx)
-    x = x.reshape(2, cout // nt, nt, cin // 16, 2, 8, 3, 3)               # (hl, nb, n, c, k8, e, ky, kx)
-    x = x.permute(1, 3, 6, 7, 0, 4, 2, 5).contiguous()                    # (nb, c, ky, kx, hl, k8, n, e)
-    return x.view(torch.uint8).reshape(-1).contiguous(), bias.float().contiguous()
+    x = torch.stack([hi, lo])                                             # (hl, G, Cin, T)
+    x = x.reshape(2, g // nt, nt, cin // 16, 2, 8, t)                     # (hl, nb, n, c, k8, e, t)
+    x = x.permute(1, 3, 6, 0, 4, 2, 5).contiguous()                       # (nb, c, t, hl, k8, n, e)
+    return x.view(torch.uint8).reshape(-1).contiguous()
+
+
+def _nt(cout):
+    assert cout % 16 == 0 and (cout <= 256 or cout % 256 == 0)
+    return cout if cout <= 256 else 256
+
+
+def pack_conv3x3(weight, bias):
+    """weight (Cout, Cin, 3, 3), bias (Cout) -> (packed, fp32 bias) for mvp_tc_conv3x3 (tap = ky*3 + kx)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    assert weight.shape[2:] == (3, 3)
+    return pack_taps(weight.reshape(cout, cin, 9), _nt(cout)), bias.float().contiguous()
+
+
+def pack_conv_taps(weight, bias):
+    """weight (Cout, Cin, kh, kw) -> (packed, bias, dy list, dx list) for mvp_tc_conv_general mode 0, 'same'-style
+    padding (kh // 2, kw // 2)."""
+    cout, cin, kh, kw = weight.shape
+    dy = [ky - kh // 2 for ky in range(kh) for _ in range(kw)]
+    dx = [kx - kw // 2 for _ in range(kh) for kx in range(kw)]
+    return pack_taps(weight.reshape(cout, cin, kh * kw), _nt(cout)), bias.float().contiguous(), dy, dx
+
+
+def pack_deconv2x2(weight, bias):
+    """ConvTranspose2d weight (Cin, Cout, 2, 2) -> (packed, bias) for mvp_tc_conv_general mode 1:
+    GEMM column (2*ky + kx) * Cout + co."""
+    cin, cout = weight.shape[0], weight.shape[1]
+    assert weight.shape[2:] == (2, 2)
+    wg = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1)
+    return pack_taps(wg, _nt(cout)), bias.float().contiguous()
+
+
+def pack_stem7x7(weight, bias):
+    """Conv2d weight (Cout, 3, 7, 7) -> (packed, bias, dy, dx) over the row-unfolded input of mvp_unfold_stem
+    (channel kx*3 + c, 21 live of 32): seven row taps."""
+    cout = weight.shape[0]
+    assert weight.shape[1:] == (3, 7, 7)
+    wg = torch.zeros(cout, 32, 7, dtype=weight.dtype, device=weight.device)
+    wg[:, :21] = weight.permute(0, 3, 1, 2).reshape(cout, 21, 7)           # (co, kx, c, ky)
+    return pack_taps(wg, _nt(cout)), bias.float().contiguous(), [ky - 3 for ky in range(7)], [0] * 7
 
 
 class Planar:
@@ -73,75 +111,76 @@ def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=False)
     return out if nhwc_out else Planar(out, x1.n, x1.h, x1.w, bias.numel())
 
 
-def _nhwc(t):
-    """logical NCHW tensor -> contiguous NHWC (no copy when the memory format already is channels-last)."""
-    return t.permute(0, 2, 3, 1).contiguous()
+def conv_general(x, packed, bias, dy, dx, stride=1, relu=True):
+    """taps (dy, dx) convolution with stride 1 or 2 on a Planar (mvp_tc_conv_general mode 0)."""
+    ho, wo = (x.h - 1) // stride + 1, (x.w - 1) // stride + 1
+    out = load_ext().fused_cuda.tc_conv_general(x.data, x.c, x.n, x.h, x.w, 0, stride, dy, dx, ho, wo, packed, bias, relu)
+    return Planar(out, x.n, ho, wo, bias.numel())
 
 
-def _nchw_view(t):
-    """contiguous NHWC tensor -> logical NCHW view in channels-last memory format (no copy)."""
-    return t.permute(0, 3, 1, 2)
+def deconv2x2(x, packed, bias, relu=True):
+    """2x2 / stride-2 transposed convolution on a Planar (mvp_tc_conv_general mode 1)."""
+    out = load_ext().fused_cuda.tc_conv_general(x.data, x.c, x.n, x.h, x.w, 1, 1, [0], [0], 2 * x.h, 2 * x.w, packed, bias, relu)
+    return Planar(out, x.n, 2 * x.h, 2 * x.w, bias.numel())
+
+
+def maxpool3x3s2(x):
+    out = load_ext().fused_cuda.maxpool3x3s2_planar(x.data, x.n, x.h, x.w, x.c)
+    return Planar(out, x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c)
 
 
 class FastUNetResNet34:
-    """Inference plan for a UNetResNet34 (this package's unet.py or the reference's, same attribute names)."""
+    """Inference plan for a UNetResNet34 (this package's unet.py or the reference's, same attribute names): every
+    layer on this package's tensor-core kernels, activations split-planar from the stem to the last decoder layer."""
 
     def __init__(self, net):
-        dev = next(net.parameters()).device
-        self.device = dev
-        cl = torch.channels_last
-
-        def cudnn_conv(conv, bn):
-            w, b = fold_conv_bn(conv, bn)
-            return w.float().contiguous(memory_format=cl), b.float().contiguous()
-
-        def mine(conv, bn):
-            w, b = fold_conv_bn(conv, bn)
-            return pack_conv3x3(w, b)
-
-        self.stem = cudnn_conv(net.encoder0, net.bn)
-        self.stem_stride, self.stem_pad = net.encoder0.stride, net.encoder0.padding
+        self.device = next(net.parameters()).device
+        e0 = net.encoder0
+        if e0.kernel_size != (7, 7) or e0.stride != (1, 1) or e0.padding != (3, 3) or e0.in_channels != 3:
+            raise RuntimeError('FastUNetResNet34: unexpected stem geometry')
+        self.stem = pack_stem7x7(*fold_conv_bn(e0, net.bn))
         self.layers = []
         for layer in (net.encoder1, net.encoder2, net.encoder3, net.encoder4):
             blocks = []
             for blk in layer:
                 e = {'stride': blk.conv1.stride[0]}
-                e['conv1'] = mine(blk.conv1, blk.bn1) if e['stride'] == 1 else cudnn_conv(blk.conv1, blk.bn1)
-                e['conv2'] = mine(blk.conv2, blk.bn2)
-                e['down'] = cudnn_conv(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
-                e['down_stride'] = blk.downsample[0].stride if blk.downsample is not None else None
+                w1, b1 = fold_conv_bn(blk.conv1, blk.bn1)
+                e['conv1'] = pack_conv3x3(w1, b1) if e['stride'] == 1 else pack_conv_taps(w1, b1)
+                e['conv2'] = pack_conv3x3(*fold_conv_bn(blk.conv2, blk.bn2))
+                e['down'] = None
+                if blk.downsample is not None:
+                    assert blk.downsample[0].stride[0] == e['stride'] and blk.downsample[0].kernel_size == (1, 1)
+                    e['down'] = pack_conv_taps(*fold_conv_bn(blk.downsample[0], blk.downsample[1]))
                 blocks.append(e)
             self.layers.append(blocks)
         self.dec = []
         for up, fuse in ((net.deconv4, net.decoder3), (net.deconv3, net.decoder2), (net.deconv2, net.decoder1), (net.deconv1, net.decoder0)):
-            wu, bu = fold_conv_bn(up[0], up[1])
-            self.dec.append({'up_w': wu.float().contiguous(memory_format=cl), 'up_b': bu.float().contiguous(),
-                             'fuse': mine(fuse[0], fuse[1])})
+            self.dec.append({'up': pack_deconv2x2(*fold_conv_bn(up[0], up[1])), 'fuse': pack_conv3x3(*fold_conv_bn(fuse[0], fuse[1]))})
 
     @torch.no_grad()
     def features_nhwc(self, x):
         """image (n,3,h,w) fp32 -> 64-channel feature map (n, h, w, 64) fp32, a view of the (padded) NHWC output."""
-        h, w = x.shape[2], x.shape[3]
+        n, _, h, w = x.shape
         pad_h, pad_w = (-h) % 16, (-w) % 16
         if pad_h or pad_w:
             x = F.pad(x, [0, pad_w, 0, pad_h])
-        x = x.contiguous(memory_format=torch.channels_last)
-        x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], self.stem_stride, self.stem_pad))
-        skips = [Planar.from_nhwc(_nhwc(x))]
-        x = Planar.from_nhwc(_nhwc(F.max_pool2d(x, kernel_size=3, stride=2, padding=1)))
+        hp, wp = h + pad_h, w + pad_w
+        x = Planar(load_ext().fused_cuda.unfold_stem(x.contiguous()), n, hp, wp, 32)
+        x = conv_general(x, *self.stem, stride=1, relu=True)
+        skips = [x]
+        x = maxpool3x3s2(x)
         for li, blocks in enumerate(self.layers):
             for e in blocks:
                 identity = x
                 if e['stride'] == 1:
                     y = conv3x3(x, *e['conv1'], relu=True)
-                else:                      # strided block: cuDNN on the merged fp32 view, results split again
-                    xf = _nchw_view(x.to_nhwc())
-                    y = Planar.from_nhwc(_nhwc(F.relu_(F.conv2d(xf, e['conv1'][0], e['conv1'][1], e['stride'], 1))))
-                    identity = Planar.from_nhwc(_nhwc(F.conv2d(xf, e['down'][0], e['down'][1], e['down_stride'], 0)))
+                else:
+                    y = conv_general(x, *e['conv1'], stride=e['stride'], relu=True)
+                if e['down'] is not None:
+                    identity = conv_general(x, *e['down'], stride=e['stride'], relu=False)
                 x = conv3x3(y, *e['conv2'], residual=identity, relu=True)
             if li < 3:
                 skips.append(x)
         for i, (d, skip) in enumerate(zip(self.dec, (skips[3], skips[2], skips[1], skips[0]))):
-            up = F.relu_(F.conv_transpose2d(_nchw_view(x.to_nhwc()), d['up_w'], d['up_b'], stride=2))
-            x = conv3x3(Planar.from_nhwc(_nhwc(up)), *d['fuse'], x2=skip, relu=True, nhwc_out=(i == 3))
+            x = conv3x3(deconv2x2(x, *d['up'], relu=True), *d['fuse'], x2=skip, relu=True, nhwc_out=(i == 3))
         return x[:, :h, :w, :]

@@ -81,3 +81,60 @@ def test_fast_unet_matches_module():
     assert got.shape == want.shape
     err = (got.double() - want).abs().max().item() / want.abs().max().item()
     assert err < 5e-5, err
+
+
+def _rel(got, want):
+    return (got.double() - want).abs().max().item() / want.abs().max().item()
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout,k', [
+    (3, 64, 80, 64, 128, 3), (3, 32, 40, 128, 256, 3), (5, 16, 20, 256, 512, 3),     # the three strided 3x3 convolutions
+    (3, 64, 80, 64, 128, 1), (5, 16, 20, 256, 512, 1), (2, 30, 37, 16, 32, 3), (3, 9, 11, 32, 16, 1)])
+def test_strided_conv_matches_float64(n, h, w, cin, cout, k):
+    from mvpnet_b200 import net2d
+    torch.manual_seed(h * 10 + k)
+    x = torch.randn(n, h, w, cin, device='cuda')
+    wt = torch.randn(cout, cin, k, k, device='cuda') / (k * cin ** 0.5)
+    b = torch.randn(cout, device='cuda')
+    packed, bias, dy, dx = net2d.pack_conv_taps(wt, b)
+    for relu in (True, False):
+        got = net2d.conv_general(net2d.Planar.from_nhwc(x), packed, bias, dy, dx, stride=2, relu=relu)
+        want = F.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), b.double(), stride=2, padding=k // 2).permute(0, 2, 3, 1)
+        want = want.clamp_min(0) if relu else want
+        assert (got.n, got.h, got.w, got.c) == tuple(want.shape)
+        assert _rel(got.to_nhwc(), want) < 2e-5
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(5, 8, 10, 512, 256), (3, 16, 20, 256, 128), (3, 32, 40, 128, 64), (2, 64, 80, 64, 64),
+                                            (3, 5, 7, 32, 16)])
+def test_deconv2x2_matches_float64(n, h, w, cin, cout):
+    from mvpnet_b200 import net2d
+    torch.manual_seed(h)
+    x = torch.randn(n, h, w, cin, device='cuda')
+    wt = torch.randn(cin, cout, 2, 2, device='cuda') / cin ** 0.5
+    b = torch.randn(cout, device='cuda')
+    packed, bias = net2d.pack_deconv2x2(wt, b)
+    got = net2d.deconv2x2(net2d.Planar.from_nhwc(x), packed, bias, relu=True)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wt.double(), b.double(), stride=2).permute(0, 2, 3, 1).clamp_min(0)
+    assert (got.n, got.h, got.w, got.c) == tuple(want.shape)
+    assert _rel(got.to_nhwc(), want) < 2e-5
+
+
+def test_stem_and_maxpool_match_float64():
+    import mvpnet_b200
+    from mvpnet_b200 import net2d
+    ext = mvpnet_b200.load_ext()
+    torch.manual_seed(3)
+    img = torch.randn(3, 3, 48, 64, device='cuda')
+    wt = torch.randn(64, 3, 7, 7, device='cuda') / 12.0
+    b = torch.randn(64, device='cuda')
+    packed, bias, dy, dx = net2d.pack_stem7x7(wt, b)
+    x = net2d.Planar(ext.fused_cuda.unfold_stem(img), 3, 48, 64, 32)
+    got = net2d.conv_general(x, packed, bias, dy, dx, stride=1, relu=True)
+    want = F.conv2d(img.double(), wt.double(), b.double(), padding=3).clamp_min(0)
+    assert _rel(got.to_nhwc(), want.permute(0, 2, 3, 1)) < 2e-5
+    for h, w in [(48, 64), (16, 20), (15, 9)]:            # 16 -> 8 rows: pair-interleaved output; odd sizes
+        t = torch.randn(3, h, w, 16, device='cuda')
+        pooled = net2d.maxpool3x3s2(net2d.Planar.from_nhwc(t))
+        ref = F.max_pool2d(net2d.Planar.from_nhwc(t).to_nhwc().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+        assert torch.equal(pooled.to_nhwc(), ref.contiguous())

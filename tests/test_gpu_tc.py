@@ -44,7 +44,7 @@ def test_pn2_full_tc_vs_simt_vs_golden(b):
     xyz = torch.from_numpy(pts.T.copy())[None].cuda().repeat(b, 1, 1)
     batch = {'points': xyz, 'feature': feat.cuda().repeat(b, 1, 1)}
     tc = run_backend('tc', lambda: net.fast_forward(batch)['seg_logit'])
-    sa_chains, fp_chains = engine._CACHE[id(net)][1]
+    sa_chains, fp_chains = engine._CACHE[(id(net), 'pn2tc')][1]
     assert all(isinstance(c, engine.TcChain) for c in sa_chains), 'tensor-core path was not selected'
     simt = run_backend('simt', lambda: net.fast_forward(batch)['seg_logit'])
     g = np.load(os.path.join(GOLD, 'pn2_full.npz'))['logit']

@@ -9,11 +9,15 @@ import torch.nn.functional as F
 from mvpnet_b200 import net2d, synthetic
 
 
-def unpack_conv3x3(packed, cin, cout):
-    nt = cout if cout <= 256 else 256
-    x = packed.view(torch.bfloat16).reshape(cout // nt, cin // 16, 3, 3, 2, 2, nt, 8)   # (nb, c, ky, kx, hl, k8, n, e)
-    x = x.permute(4, 0, 6, 1, 5, 7, 2, 3).reshape(2, cout, cin, 3, 3).float()
+def unpack_taps(packed, cin, g, t, nt):
+    x = packed.view(torch.bfloat16).reshape(g // nt, cin // 16, t, 2, 2, nt, 8)          # (nb, c, t, hl, k8, n, e)
+    x = x.permute(3, 0, 5, 1, 4, 6, 2).reshape(2, g, cin, t).float()
     return x[0], x[1]
+
+
+def unpack_conv3x3(packed, cin, cout):
+    hi, lo = unpack_taps(packed, cin, cout, 9, cout if cout <= 256 else 256)
+    return hi.reshape(cout, cin, 3, 3), lo.reshape(cout, cin, 3, 3)
 
 
 def emulated_conv(x1, x2, packed, bias, residual, relu):
@@ -25,6 +29,30 @@ def emulated_conv(x1, x2, packed, bias, residual, relu):
     if relu:
         y = y.clamp_min(0)
     return y.float().contiguous()
+
+
+def emulated_general(x, mode, stride, dy, dx, ho, wo, packed, bias, relu):
+    """x (N, Hi, Wi, Cin) fp32; the documented semantics of mvp_tc_conv_general, tap by tap."""
+    n, hi_, wi_, cin = x.shape
+    cout = bias.numel()
+    nt = cout if cout <= 256 else 256
+    g = 4 * cout if mode else cout
+    whi, wlo = unpack_taps(packed, cin, g, len(dy), nt)
+    wg = (whi + wlo).double()
+    xd = x.double()
+    if mode:
+        y = torch.einsum('nhwc,gc->nhwg', xd, wg[:, :, 0]).reshape(n, hi_, wi_, 2, 2, cout)      # (.., ky, kx, co)
+        y = y.permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * hi_, 2 * wi_, cout) + bias.double()
+    else:
+        pad = 8
+        xp = F.pad(xd, [0, 0, pad, pad + stride * wo, pad, pad + stride * ho])
+        y = torch.zeros(n, ho, wo, cout, dtype=torch.float64) + bias.double()
+        for t in range(len(dy)):
+            ys = pad + dy[t]
+            xs = pad + dx[t]
+            patch = xp[:, ys:ys + stride * ho:stride, xs:xs + stride * wo:stride, :]
+            y = y + torch.einsum('nhwc,gc->nhwg', patch, wg[:, :, t])
+    return (y.clamp_min(0) if relu else y).float().contiguous()
 
 
 def test_pack_round_trip():
@@ -62,6 +90,24 @@ def test_plan_matches_module_features(monkeypatch):
             y = emulated_conv(x1.reshape(n, h, w, c1), None if x2 is None else x2.reshape(n, h, w, c2), packed, bias,
                               None if residual is None else residual.reshape(n, h, w, cout), relu)
             return y if nhwc_out else y.reshape(-1)
+
+        @staticmethod
+        def tc_conv_general(x, cin, n, hi_, wi_, mode, stride, dy, dx, ho, wo, packed, bias, relu):
+            return emulated_general(x.reshape(n, hi_, wi_, cin), mode, stride, dy, dx, ho, wo, packed, bias, relu).reshape(-1)
+
+        @staticmethod
+        def unfold_stem(img):
+            n, _, h, w = img.shape
+            out = torch.zeros(n, h, w, 32)
+            xp = F.pad(img, [3, 3])
+            for kx in range(7):
+                out[..., kx * 3:kx * 3 + 3] = xp[:, :, :, kx:kx + w].permute(0, 2, 3, 1)
+            return out.reshape(-1)
+
+        @staticmethod
+        def maxpool3x3s2_planar(x, n, h, w, c):
+            y = F.max_pool2d(x.reshape(n, h, w, c).permute(0, 3, 1, 2), 3, 2, 1)
+            return y.permute(0, 2, 3, 1).contiguous().reshape(-1)
 
     class _Ext:
         fused_cuda = _Fused
