@@ -20,6 +20,7 @@ op-by-op CUDA composition in modules.py (still this package's kernels).
 """
 import contextlib
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -178,12 +179,16 @@ _CACHE = {}
 
 
 def _cached(module, key, build):
+    """Per-module cache of packed weights / plans.  Keyed by id(module) AND checked against a weak reference: ids are
+    reused after garbage collection, and a stale hit would silently run another model's weights."""
     sig = (key, tuple(int(t._version) for t in module.state_dict().values()),
            next(module.parameters()).device, module.training)
     hit = _CACHE.get((id(module), key))
-    if hit is None or hit[0] != sig:
-        hit = (sig, build())
+    if hit is None or hit[0] != sig or hit[2]() is not module:
+        hit = (sig, build(), weakref.ref(module))
         _CACHE[(id(module), key)] = hit
+        for k in [k for k, v in _CACHE.items() if v[2]() is None]:      # drop entries of dead modules
+            del _CACHE[k]
     return hit[1]
 
 
