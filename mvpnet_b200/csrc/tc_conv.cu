@@ -43,8 +43,9 @@ constexpr int SLOT_BYTES = 2 * SLOT_HALF;     // 12800
 constexpr int MAX_TM = 4;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_ASETS = 3;
-constexpr int EPI_THREADS = 128;
-constexpr int THREADS = EPI_THREADS + 96;
+constexpr int EPI_WARPS = 8;                    // two per TMEM lane quarter: alternate 16-column chunks
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + 96;      // + MMA issuer, patch producer, weight producer warps
 
 struct ConvArgs {
   CUtensorMap m1h, m1l, m2h, m2l;   // split-planar inputs: hi / lo plane of x1 and x2
@@ -66,6 +67,7 @@ struct ConvArgs {
   int asets;                        // patch ring depth (sets of TM slots)
   int nchunks;                      // (C1 + C2) / 16
   int stages;                       // weight ring depth
+  int tps;                          // taps per weight stage: 1, 3 (one filter row) or 9 (a whole chunk)
   int tmem_cols;
   int dbg;                          // MVPNET_B200_CONV_DBG experiment bits (timing studies only; results are wrong)
 };
@@ -122,10 +124,11 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // shared memory: [asets][TM] patches | [stages] weight ring | barriers
   unsigned char *a_base = smem;
-  const size_t stage_bytes = (size_t)64 * a.Nt;
+  const size_t tap_bytes = (size_t)64 * a.Nt, stage_bytes = tap_bytes * a.tps;
   unsigned char *b_base = a_base + (size_t)a.asets * a.TM * SLOT_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)a.stages * stage_bytes);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2 * MAX_ASETS + 4);
+  float *s_bias = reinterpret_cast<float *>(bars + 32);        // [Cout]: the epilogue reads it once per chunk (L1 is a few KB here)
   const uint32_t bar_bfull = smem_u32(bars), bar_bempty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + MAX_ASETS);
   const uint32_t bar_accfull = smem_u32(bars + 2 * MAX_STAGES + 2 * MAX_ASETS), bar_accempty = bar_accfull + 16;
@@ -136,7 +139,8 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
     for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, EPI_THREADS); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  for (int i = tid; i < a.Cout; i += THREADS) s_bias[i] = a.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -148,68 +152,82 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   const uint32_t S = (uint32_t)a.stages, AS = (uint32_t)a.asets, NA = (uint32_t)a.nacc;
   const int pair = a.ipt == 2;
 
-  if (warp < 4) {
-    // =========================== epilogue: thread = TMEM lane = pixel ================================================
-    const int row = warp * 32 + lane, g = row >> 3, xx = row & 7;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (warp < EPI_WARPS) {
+    // =========================== epilogue: thread = TMEM lane = pixel; the two warps of a lane quarter take
+    //                             alternate 16-column chunks ==================================================
+    // The (tile, chunk) items of a work item form one software pipeline: the residual of item i + 1 is in flight
+    // while item i is finished, and the first item's residual is requested BEFORE the accumulator barrier.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane, g = row >> 3, xx = row & 7;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int C8o = a.Cout >> 3;
+    const size_t slab_stride = (size_t)a.H * a.W * 8 * (pair ? 2 : 1);           // elements between slabs of one image
+    const int c0 = half * 16, cpt = (a.Nt - c0 + 31) / 32;                       // this thread's chunks per tile
+    struct Item { size_t pbase, fbase; bool ok; };
+    auto locate = [&](long long tile, int nb) {
+      Item r;
+      const TileCoord tc_ = tile_coord(a, tile);
+      const int img = pair ? tc_.n + (g & 1) : tc_.n;
+      const int y = pair ? (g >> 1) : tc_.y0 + g;
+      const int x = tc_.x0 + xx;
+      r.ok = img < a.N && y < a.H && x < a.W && !(a.dbg & 2);
+      r.pbase = r.ok ? planar_off(img, nb * (a.Nt >> 3), y, x, C8o, a.H, a.W, pair) : 0;
+      r.fbase = r.ok ? (((size_t)img * a.H + y) * a.W + x) * a.Cout + (size_t)nb * a.Nt : 0;
+      return r;
+    };
+    auto load_res = [&](const Item &p, int c, uint4 (&rh)[2], uint4 (&rl)[2]) {
+      if (a.res != nullptr && p.ok) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const size_t o = p.pbase + (size_t)((c >> 3) + s) * slab_stride;
+          rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + o));
+          rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + o));
+        }
+      }
+    };
     uint32_t it = 0;
     for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++it) {
       const int nb = (int)(w / a.ngroups);
       const long long group = w - (long long)nb * a.ngroups;
       const uint32_t set = it % NA;
+      const long long left = a.ntiles - group * a.TM;
+      const int nt = left < a.TM ? (int)left : a.TM;
+      const float *bias_s = s_bias + nb * a.Nt;
+      Item cur = locate(group * a.TM, nb);
+      uint4 rh[2], rl[2];
+      if (cpt > 0) load_res(cur, c0, rh, rl);
       mbar_wait(bar_accfull + 8 * set, (it / NA) & 1u);
       tc_fence_after();
-      for (int t = 0; t < a.TM; ++t) {
-        const long long tile = group * a.TM + t;
-        if (tile >= a.ntiles) break;
-        const TileCoord tc_ = tile_coord(a, tile);
-        const int img = pair ? tc_.n + (g & 1) : tc_.n;
-        const int y = pair ? (g >> 1) : tc_.y0 + g;
-        const int x = tc_.x0 + xx;
-        const bool ok = img < a.N && y < a.H && x < a.W && !(a.dbg & 2);
-        const size_t slab_stride = (size_t)a.H * a.W * 8 * (pair ? 2 : 1);       // elements between slabs of one image
-        const size_t pbase = ok ? planar_off(img, nb * (a.Nt >> 3), y, x, C8o, a.H, a.W, pair) : 0;
-        const size_t fbase = ok ? (((size_t)img * a.H + y) * a.W + x) * a.Cout + (size_t)nb * a.Nt : 0;
+      for (int t = 0; t < nt && cpt > 0; ++t) {
         const uint32_t t_acc = t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
+        Item nxt = cur;
+        if (t + 1 < nt) nxt = locate(group * a.TM + t + 1, nb);
         uint32_t rn[16];
-        uint4 rh[2], rl[2];
-        tmem_ld16_issue(t_acc, rn);
-        if (a.res != nullptr && ok) {
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + pbase + s * slab_stride));
-            rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + pbase + s * slab_stride));
-          }
-        }
-        for (int c = 0; c < a.Nt; c += 16) {
+        tmem_ld16_issue(t_acc + (uint32_t)c0, rn);
+        for (int c = c0; c < a.Nt; c += 32) {
           float v[16];
           tmem_ld_wait(rn);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
-          if (c + 16 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 16), rn);
-          const float4 *bp = reinterpret_cast<const float4 *>(a.bias + nb * a.Nt + c);
+          if (c + 32 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 32), rn);
+          const float4 *bp = reinterpret_cast<const float4 *>(bias_s + c);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bq = __ldg(bp + q);
+            const float4 bq = bp[q];
             v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
-          if (ok) {
-            if (a.res != nullptr) {
+          if (a.res != nullptr) {
+            if (cur.ok) {
               float r0[8], r1[8];
               unpack8(rh[0], rl[0], r0);
               unpack8(rh[1], rl[1], r1);
 #pragma unroll
               for (int q = 0; q < 8; ++q) { v[q] += r0[q]; v[8 + q] += r1[q]; }
-              if (c + 16 < a.Nt) {           // next chunk's residual is in flight while this one is finished
-                const size_t o = pbase + (size_t)((c + 16) >> 3) * slab_stride;
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                  rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + o + s * slab_stride));
-                  rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + o + s * slab_stride));
-                }
-              }
             }
+            if (c + 32 < a.Nt) load_res(cur, c + 32, rh, rl);          // next item: same tile, next chunk ...
+            else if (t + 1 < nt) load_res(nxt, c0, rh, rl);              // ... or the first chunk of the next tile
+          }
+          if (cur.ok) {
             if (a.relu) {
 #pragma unroll
               for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
@@ -220,126 +238,170 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
                 uint32_t h[4], l[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) split_pair(v[8 * s + 2 * q], v[8 * s + 2 * q + 1], h[q], l[q]);
-                const size_t o = pbase + (size_t)((c >> 3) + s) * slab_stride;
+                const size_t o = cur.pbase + (size_t)((c >> 3) + s) * slab_stride;
                 *reinterpret_cast<uint4 *>(a.out_p + o) = make_uint4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<uint4 *>(a.out_p + a.plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
               }
             }
             if (a.out_f != nullptr) {
-              float4 *op = reinterpret_cast<float4 *>(a.out_f + fbase + c);
+              float4 *op = reinterpret_cast<float4 *>(a.out_f + cur.fbase + c);
 #pragma unroll
               for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
           }
         }
+        cur = nxt;
       }
       tc_fence_before();
       mbar_arrive(bar_accempty + 8 * set);
     }
-  } else if (warp == 4) {
+  } else if (warp == EPI_WARPS) {
     // =========================== MMA issuer ===========================================================================
     // The WHOLE warp walks the loops (every value is warp-uniform, so descriptors live in uniform registers) and one
     // elected lane issues; a loop under `if (lane == 0)` makes ptxas wrap every tcgen05 instruction in a
     // thread-by-thread broadcast loop, which costs more than the MMAs of a narrow layer take to execute.
     const uint32_t idesc = make_idesc(128, a.Nt);
     const uint32_t a_s = smem_u32(a_base), b_s = smem_u32(b_base);
+    // descriptors as (low word, high word): the low word holds the start address (>> 4, bits 0-13) and the K-direction
+    // stride; stepping to another tap / plane / tile / stage is one 32-bit add on the low word.  Ring positions and
+    // phases are running counters: this warp's instruction stream is the pacing item of narrow layers (a K-step of
+    // three N = 64 MMAs executes in ~100 cycles), so no division, modulo or 64-bit arithmetic is left in the loops.
     const uint64_t adesc0 = make_desc(0, slab_bytes, HC * 16), bdesc0 = make_desc(0, (uint32_t)a.Nt * 16u, 128);
-    uint32_t a_it = 0, b_it = 0, w_it = 0;
+    const uint32_t a_lo0 = (uint32_t)adesc0 + (a_s >> 4), a_hi32 = (uint32_t)(adesc0 >> 32);
+    const uint32_t b_lo0 = (uint32_t)bdesc0 + (b_s >> 4), b_hi32 = (uint32_t)(bdesc0 >> 32);
+    const uint32_t set16 = (uint32_t)(a.TM * SLOT_BYTES) >> 4, stage16 = (uint32_t)stage_bytes >> 4, tap16 = (uint32_t)tap_bytes >> 4, lo_of_hi = 2u * (uint32_t)a.Nt;
+    const uint32_t row16 = (uint32_t)(a.ipt * HC);            // one image row of the patch, in 16-byte units
+    auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    uint32_t ss = 0, a_ph = 0, s = 0, b_ph = 0, set = 0, acc_ph = 0, w_it = 0;
+    long long group = blockIdx.x % a.ngroups;
     for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++w_it) {
-      const long long group = w % a.ngroups;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
-      const uint32_t set = w_it % NA;
-      if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, ((w_it / NA) - 1u) & 1u);
+      group += gridDim.x;
+      while (group >= a.ngroups) group -= a.ngroups;
+      if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, acc_ph ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + set * (uint32_t)(a.TM * a.Nt);
-      for (int c = 0; c < a.nchunks; ++c, ++a_it) {
-        const uint32_t ss = a_it % AS;
-        mbar_wait(bar_afull + 8 * ss, (a_it / AS) & 1u);
-        const uint32_t a_set = a_s + ss * (uint32_t)(a.TM * SLOT_BYTES);
-        for (int tap = 0; tap < 9; ++tap, ++b_it) {
-          const uint32_t s = b_it % S;
-          mbar_wait(bar_bfull + 8 * s, (b_it / S) & 1u);
-          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-          const uint32_t a_tap = a_set + (uint32_t)(((a.ipt * (1 + dy)) * HC + (1 + dx)) * 16);
-          const uint32_t b_hi = b_s + s * (uint32_t)stage_bytes;
-          const uint64_t bh = bdesc0 | (uint64_t)((b_hi >> 4) & 0x3fffu), bl = bdesc0 | (uint64_t)(((b_hi + 32u * (uint32_t)a.Nt) >> 4) & 0x3fffu);
-          if (elect_one()) {
-            for (int t = 0; t < nt && !(a.dbg & 16); ++t) {
-              const uint32_t a_hi = a_tap + (uint32_t)(t * SLOT_BYTES);
-              const uint64_t ah = adesc0 | (uint64_t)((a_hi >> 4) & 0x3fffu), al = adesc0 | (uint64_t)(((a_hi + SLOT_HALF) >> 4) & 0x3fffu);
-              const uint32_t d = d0 + (uint32_t)(t * a.Nt);
-              umma_bf16(d, ah, bh, idesc, (c == 0 && tap == 0) ? 0u : 1u);
-              if (!(a.dbg & 1)) {
-                umma_bf16(d, ah, bl, idesc, 1u);
-                umma_bf16(d, al, bh, idesc, 1u);
-              }
+      uint32_t first = 0u;
+      for (int c = 0; c < a.nchunks; ++c) {
+        mbar_wait(bar_afull + 8 * ss, a_ph);
+        uint32_t a_tap_lo = a_lo0 + ss * set16;               // tap (-1, -1): the patch origin
+        uint32_t b_lo = 0;
+        int in_stage = 0;                                     // taps of the current weight stage already used
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            if (in_stage == 0) {
+              mbar_wait(bar_bfull + 8 * s, b_ph);
+              b_lo = b_lo0 + s * stage16;
             }
-            umma_commit(bar_bempty + 8 * s);
+            const uint64_t bh = desc64(b_lo, b_hi32), bl = desc64(b_lo + lo_of_hi, b_hi32);
+            const bool last = in_stage + 1 == a.tps;
+            if (elect_one()) {
+              if (!(a.dbg & 16)) {
+#pragma unroll
+                for (int t = 0; t < MAX_TM; ++t) {
+                  if (t < nt) {
+                    const uint32_t lo = a_tap_lo + (uint32_t)dx + (uint32_t)(t * (SLOT_BYTES >> 4));
+                    const uint64_t ah = desc64(lo, a_hi32), al = desc64(lo + (SLOT_HALF >> 4), a_hi32);
+                    const uint32_t d = d0 + (uint32_t)(t * a.Nt);
+                    umma_bf16(d, ah, bh, idesc, first);
+                    umma_bf16(d, ah, bl, idesc, 1u);
+                    umma_bf16(d, al, bh, idesc, 1u);
+                  }
+                }
+              }
+              if (last) { if (a.dbg & 64) mbar_arrive(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s); }
+            }
+            __syncwarp();
+            first = 1u;
+            b_lo += tap16;
+            if (last) { in_stage = 0; if (++s == S) { s = 0; b_ph ^= 1u; } } else { ++in_stage; }
           }
-          __syncwarp();
+          a_tap_lo += row16;
         }
         if (elect_one()) umma_commit(bar_aempty + 8 * ss);
         __syncwarp();
+        if (++ss == AS) { ss = 0; a_ph ^= 1u; }
       }
       if (elect_one()) umma_commit(bar_accfull + 8 * set);
       __syncwarp();
+      if (++set == NA) { set = 0; acc_ph ^= 1u; }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
     // =========================== patch producer: one TMA box per (tile, chunk, plane) ================================
     const uint32_t box_bytes = 2u * slab_bytes;
     const uint32_t a_s = smem_u32(a_base);
-    uint32_t it = 0;
+    uint32_t ss = 0, ph = 0, it = 0;
     for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
       const long long group = w % a.ngroups;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
+      int cx[MAX_TM], cy[MAX_TM], cn[MAX_TM];               // tile coordinates: once per work item
+#pragma unroll
+      for (int t = 0; t < MAX_TM; ++t) {
+        const TileCoord tc_ = tile_coord(a, group * a.TM + (t < nt ? t : 0));
+        cx[t] = (tc_.x0 - 1) * 8; cy[t] = tc_.y0 - 1; cn[t] = pair ? (tc_.n >> 1) : tc_.n;
+      }
       for (int c = 0; c < a.nchunks; ++c, ++it) {
-        const uint32_t ss = it % AS;
-        if (it >= AS) mbar_wait(bar_aempty + 8 * ss, ((it / AS) - 1u) & 1u);
+        if (it >= AS) mbar_wait(bar_aempty + 8 * ss, ph ^ 1u);
         const int k0 = c * 16;
         const bool first = k0 < a.C1;
         const CUtensorMap *mh = first ? &a.m1h : &a.m2h, *ml = first ? &a.m1l : &a.m2l;
         const int C8 = (first ? a.C1 : a.C2) >> 3, s0 = (first ? k0 : k0 - a.C1) >> 3;
+        const uint32_t bar = bar_afull + 8 * ss, dst0 = a_s + ss * (uint32_t)(a.TM * SLOT_BYTES);
         if (elect_one()) {
-          mbar_expect_tx(bar_afull + 8 * ss, (uint32_t)nt * 2u * box_bytes);
-          for (int t = 0; t < nt; ++t) {
-            const TileCoord tc_ = tile_coord(a, group * a.TM + t);
-            const uint32_t dst = a_s + (ss * (uint32_t)a.TM + (uint32_t)t) * SLOT_BYTES;
-            if (!pair) {                 // dims (8 * W, H, C8 * N)
-              tma_load_3d(dst, mh, (tc_.x0 - 1) * 8, tc_.y0 - 1, tc_.n * C8 + s0, bar_afull + 8 * ss);
-              tma_load_3d(dst + SLOT_HALF, ml, (tc_.x0 - 1) * 8, tc_.y0 - 1, tc_.n * C8 + s0, bar_afull + 8 * ss);
-            } else {                     // dims (8 * W, 2, H, C8 * N/2)
-              tma_load_4d(dst, mh, (tc_.x0 - 1) * 8, 0, -1, (tc_.n >> 1) * C8 + s0, bar_afull + 8 * ss);
-              tma_load_4d(dst + SLOT_HALF, ml, (tc_.x0 - 1) * 8, 0, -1, (tc_.n >> 1) * C8 + s0, bar_afull + 8 * ss);
+          if (a.dbg & 32) {                                  // timing study: no patch traffic
+            mbar_arrive(bar);
+          } else {
+            mbar_expect_tx(bar, (uint32_t)nt * 2u * box_bytes);
+#pragma unroll
+            for (int t = 0; t < MAX_TM; ++t) {
+              if (t < nt) {
+                const uint32_t dst = dst0 + (uint32_t)(t * SLOT_BYTES);
+                if (!pair) {               // dims (8 * W, H, C8 * N)
+                  tma_load_3d(dst, mh, cx[t], cy[t], cn[t] * C8 + s0, bar);
+                  tma_load_3d(dst + SLOT_HALF, ml, cx[t], cy[t], cn[t] * C8 + s0, bar);
+                } else {                   // dims (8 * W, 2, H, C8 * N/2)
+                  tma_load_4d(dst, mh, cx[t], 0, -1, cn[t] * C8 + s0, bar);
+                  tma_load_4d(dst + SLOT_HALF, ml, cx[t], 0, -1, cn[t] * C8 + s0, bar);
+                }
+              }
             }
           }
         }
         __syncwarp();
+        if (++ss == AS) { ss = 0; ph ^= 1u; }
       }
     }
   } else {
     // =========================== weight producer ======================================================================
     const uint32_t b_s = smem_u32(b_base);
-    uint32_t it = 0;
+    const uint32_t nbytes = (a.dbg & 4) ? 16u : (uint32_t)stage_bytes;
+    const int per_work = a.nchunks * 9 / a.tps;
+    uint32_t s = 0, ph = 0, it = 0;
     for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
       const int nb = (int)(w / a.ngroups);
-      const unsigned char *wsrc = a.wp + (size_t)nb * a.nchunks * 9 * stage_bytes;
-      for (int j = 0; j < a.nchunks * 9; ++j, ++it) {
-        const uint32_t s = it % S;
-        if (it >= S) mbar_wait(bar_bempty + 8 * s, ((it / S) - 1u) & 1u);
+      const unsigned char *wsrc = a.wp + (size_t)nb * per_work * stage_bytes;
+      for (int j = 0; j < per_work; ++j, ++it, wsrc += stage_bytes) {
+        if (it >= S) mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
         if (elect_one()) {
-          const uint32_t nbytes = (a.dbg & 4) ? 16u : (uint32_t)stage_bytes;
-          mbar_expect_tx(bar_bfull + 8 * s, nbytes);
-          bulk_g2s(b_s + s * (uint32_t)stage_bytes, wsrc + (size_t)j * stage_bytes, nbytes, bar_bfull + 8 * s);
+          if (a.dbg & 128) {
+            mbar_arrive(bar_bfull + 8 * s);
+          } else {
+            mbar_expect_tx(bar_bfull + 8 * s, nbytes);
+            bulk_g2s(b_s + s * (uint32_t)stage_bytes, wsrc, nbytes, bar_bfull + 8 * s);
+          }
         }
         __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 // ---- split-planar <-> fp32 NHWC (the boundary to the layers that still run on cuDNN) --------------------------------
@@ -477,11 +539,16 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
   a.asets = tcc::MAX_ASETS;
   a.stages = tcc::MAX_STAGES;
+  // taps per weight stage: a whole chunk (9 taps) for narrow layers, one filter row otherwise — every stage costs
+  // the issuer one barrier round trip, which a single N <= 64 tap (12 short MMAs) does not cover
+  a.tps = a.Nt <= 64 ? 9 : 3;
   {
     const char *e = getenv("MVPNET_B200_CONV_DBG");
     a.dbg = e ? atoi(e) : 0;
     const char *st = getenv("MVPNET_B200_CONV_STAGES");
     if (st && atoi(st) >= 2 && atoi(st) <= tcc::MAX_STAGES) a.stages = atoi(st);
+    const char *tp = getenv("MVPNET_B200_CONV_TPS");
+    if (tp && (atoi(tp) == 1 || atoi(tp) == 3 || atoi(tp) == 9)) a.tps = atoi(tp);
     const char *tm = getenv("MVPNET_B200_CONV_TM");
     if (tm && atoi(tm) >= 1 && atoi(tm) <= tcc::MAX_TM && atoi(tm) * a.Nt <= 512) {
       a.TM = atoi(tm);
@@ -491,9 +558,11 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
       while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
     }
   }
-  auto smem_of = [&]() { return (size_t)a.asets * a.TM * tcc::SLOT_BYTES + (size_t)a.stages * 64 * a.Nt + 512; };
-  while (a.stages > 4 && smem_of() > tc::SMEM_CAP) --a.stages;
+  auto smem_of = [&]() { return (size_t)a.asets * a.TM * tcc::SLOT_BYTES + (size_t)a.stages * a.tps * 64 * a.Nt + 512 + (size_t)a.Cout * 4; };
+  while (a.stages > 3 && smem_of() > tc::SMEM_CAP) --a.stages;
   while (a.asets > 2 && smem_of() > tc::SMEM_CAP) --a.asets;
+  while (a.stages > 2 && smem_of() > tc::SMEM_CAP) --a.stages;
+  if (smem_of() > tc::SMEM_CAP && a.tps > 1) { a.tps = a.tps == 9 ? 3 : 1; a.stages = tcc::MAX_STAGES; while (a.stages > 2 && smem_of() > tc::SMEM_CAP) --a.stages; }
   const size_t smem = smem_of();
   MVP_REQUIRE(smem <= tc::SMEM_CAP, MVP_ERR_UNSUPPORTED, "tc_conv3x3: shared memory budget exceeded");
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -503,8 +572,8 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   if (grid > nworks) grid = nworks;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
   if (debug)
-    fprintf(stderr, "[tc_conv3x3] N=%d H=%d W=%d Cin=%d+%d Cout=%d Nt=%d ipt=%d tiles=%lld TM=%d nacc=%d works=%lld asets=%d stages=%d smem=%zu tmem=%d\n",
-            a.N, a.H, a.W, a.C1, a.C2, a.Cout, a.Nt, a.ipt, a.ntiles, a.TM, a.nacc, nworks, a.asets, a.stages, smem, a.tmem_cols);
+    fprintf(stderr, "[tc_conv3x3] N=%d H=%d W=%d Cin=%d+%d Cout=%d Nt=%d ipt=%d tiles=%lld TM=%d nacc=%d works=%lld asets=%d stages=%d tps=%d smem=%zu tmem=%d\n",
+            a.N, a.H, a.W, a.C1, a.C2, a.Cout, a.Nt, a.ipt, a.ntiles, a.TM, a.nacc, nworks, a.asets, a.stages, a.tps, smem, a.tmem_cols);
   tcc::tc_conv3x3_kernel<<<(unsigned)grid, tcc::THREADS, smem, (cudaStream_t)stream>>>(a);
   return launch_status("tc_conv3x3");
 }

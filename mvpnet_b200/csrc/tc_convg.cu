@@ -24,6 +24,7 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map
 
 constexpr int G_MAX_TAPS = 9;
 constexpr int G_MAX_STAGES = 6;
+constexpr int G_EPI_THREADS = 128, G_THREADS = G_EPI_THREADS + 96;
 
 struct ConvGArgs {
   CUtensorMap mh, ml;               // input planes
@@ -48,7 +49,7 @@ struct ConvGArgs {
   int TM, nacc, astages, stages, tmem_cols;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, 1)
 tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -60,6 +61,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
   unsigned char *b_base = a_base + (size_t)a.astages * a_stage;
   uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)a.stages * b_stage);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * G_MAX_STAGES + 4);
+  float *s_bias = reinterpret_cast<float *>(bars + 32);          // [Cout]
   const uint32_t bar_bfull = smem_u32(bars), bar_bempty = bar_bfull + 8 * G_MAX_STAGES;
   const uint32_t bar_afull = bar_bempty + 8 * G_MAX_STAGES, bar_aempty = bar_afull + 8 * G_MAX_STAGES;
   const uint32_t bar_accfull = bar_aempty + 8 * G_MAX_STAGES, bar_accempty = bar_accfull + 16;
@@ -69,10 +71,11 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1);
       mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, EPI_THREADS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, G_EPI_THREADS); }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  for (int i = tid; i < a.Cout; i += G_THREADS) s_bias[i] = a.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -116,10 +119,10 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
           if (c + 16 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 16), rn);
-          const float4 *bp = reinterpret_cast<const float4 *>(a.bias + co0 + c);
+          const float4 *bp = reinterpret_cast<const float4 *>(s_bias + co0 + c);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 bq = __ldg(bp + q);
+            const float4 bq = bp[q];
             v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
           }
           if (a.relu) {
@@ -377,7 +380,7 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   if (int rc = tcc::make_plane_map_g(&a.ml, (const __nv_bfloat16 *)x + Np_in * Cin * Hi * Wi, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
   const size_t a_stage = (size_t)a.TM * a.KC * 512, b_stage = (size_t)a.KC * a.Nt * 4;
   a.astages = a.stages = tcc::G_MAX_STAGES;
-  auto smem_of = [&]() { return a.astages * a_stage + a.stages * b_stage + 512; };
+  auto smem_of = [&]() { return a.astages * a_stage + a.stages * b_stage + 512 + (size_t)a.Cout * 4; };
   while (smem_of() > tc::SMEM_CAP && (a.astages > 2 || a.stages > 2)) {
     if (a.astages >= a.stages && a.astages > 2) --a.astages; else if (a.stages > 2) --a.stages; else --a.astages;
   }
@@ -392,7 +395,7 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   if (debug)
     fprintf(stderr, "[tc_conv_general] N=%d in=%dx%d out=%dx%d Cin=%d Cout=%d mode=%d stride=%d taps=%d Nt=%d NB=%d KC=%d tiles=%lld TM=%d nacc=%d works=%lld astages=%d stages=%d smem=%zu\n",
             a.N, a.Hi, a.Wi, a.Ho, a.Wo, a.Cin, a.Cout, mode, stride, ntaps, a.Nt, a.NB, a.KC, a.ntiles, a.TM, a.nacc, nworks, a.astages, a.stages, smem);
-  tcc::tc_convg_kernel<<<(unsigned)grid, tcc::THREADS, smem, (cudaStream_t)stream>>>(a);
+  tcc::tc_convg_kernel<<<(unsigned)grid, tcc::G_THREADS, smem, (cudaStream_t)stream>>>(a);
   return launch_status("tc_conv_general");
 }
 

@@ -69,20 +69,26 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// try_wait suspends in hardware for a bounded time per attempt; a protocol error traps instead of hanging the GPU
+// Polls with test_wait (returns at once) rather than try_wait (suspends the thread for a hardware-chosen quantum: the
+// wake-up after a barrier that completes mid-suspension cost ~500 cycles per blocking wait in the convolution's
+// stage ring).  MVPNET_B200_TRYWAIT=1 at build time restores try_wait.  A protocol error traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok, spins = 0;
   do {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
+#ifdef MVPNET_B200_TRYWAIT
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!ok && ++spins > (1u << 24)) __trap();
+    if (!ok && ++spins > (1u << 26)) __trap();
   } while (!ok);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
