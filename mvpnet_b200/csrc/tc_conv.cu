@@ -70,6 +70,7 @@ struct ConvArgs {
   int tps;                          // taps per weight stage: 1, 3 (one filter row) or 9 (a whole chunk)
   int tmem_cols;
   int dbg;                          // MVPNET_B200_CONV_DBG experiment bits (timing studies only; results are wrong)
+  unsigned int *sched;              // {next work item, retired CTAs}: zero between launches (self re-arming)
 };
 
 struct TileCoord { int n, y0, x0; };
@@ -118,6 +119,42 @@ __device__ __forceinline__ void unpack8(const uint4 h, const uint4 l, float (&v)
   }
 }
 
+// ---- dynamic work distribution ---------------------------------------------------------------------------------------
+// Work items are handed out by a global counter instead of blockIdx striding: a CTA that starts late (its SM was busy
+// with a kernel of the geometry stream: FPS holds 32 SMs for over a millisecond) simply takes fewer items, and the
+// last wave is shared by whoever is free.  One warp of the CTA (the patch producer) draws the indices and publishes
+// them to the other roles through a 4-deep shared-memory ring guarded by mbarriers.
+constexpr int SCHED_DEPTH = 4;
+constexpr int SCHED_CONSUMERS = 2 + EPI_WARPS;        // MMA issuer, weight producer, epilogue warps (one arrival each)
+
+__device__ __forceinline__ int sched_produce(uint32_t k, volatile int *ring, uint32_t bar_full, uint32_t bar_empty, unsigned int *counter) {
+  const uint32_t slot = k & (SCHED_DEPTH - 1);
+  if (k >= SCHED_DEPTH) mbar_wait(bar_empty + 8 * slot, ((k / SCHED_DEPTH) - 1u) & 1u);
+  if (elect_one()) {
+    ring[slot] = (int)atomicAdd(counter, 1u);
+    mbar_arrive(bar_full + 8 * slot);
+  }
+  __syncwarp();
+  return ring[slot];
+}
+__device__ __forceinline__ int sched_consume(uint32_t k, volatile int *ring, uint32_t bar_full, uint32_t bar_empty) {
+  const uint32_t slot = k & (SCHED_DEPTH - 1);
+  mbar_wait(bar_full + 8 * slot, (k / SCHED_DEPTH) & 1u);
+  const int w = ring[slot];
+  __syncwarp();
+  if (elect_one()) mbar_arrive(bar_empty + 8 * slot);
+  __syncwarp();
+  return w;
+}
+// the last CTA to run dry re-arms the counter pair for the next launch that uses it
+__device__ __forceinline__ void sched_retire(unsigned int *counter) {
+  if (elect_one()) {
+    const unsigned int done = atomicAdd(counter + 1, 1u);
+    if (done == gridDim.x - 1) { counter[0] = 0u; counter[1] = 0u; __threadfence(); }
+  }
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -128,7 +165,9 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   unsigned char *b_base = a_base + (size_t)a.asets * a.TM * SLOT_BYTES;
   uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)a.stages * stage_bytes);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2 * MAX_ASETS + 4);
-  float *s_bias = reinterpret_cast<float *>(bars + 32);        // [Cout]: the epilogue reads it once per chunk (L1 is a few KB here)
+  volatile int *s_ring = reinterpret_cast<volatile int *>(bars + 28);      // [SCHED_DEPTH] work indices
+  const uint32_t bar_sfull = smem_u32(bars + 32), bar_sempty = smem_u32(bars + 32 + SCHED_DEPTH);
+  float *s_bias = reinterpret_cast<float *>(bars + 48);        // [Cout]: the epilogue reads it once per chunk (L1 is a few KB here)
   const uint32_t bar_bfull = smem_u32(bars), bar_bempty = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_afull = smem_u32(bars + 2 * MAX_STAGES), bar_aempty = smem_u32(bars + 2 * MAX_STAGES + MAX_ASETS);
   const uint32_t bar_accfull = smem_u32(bars + 2 * MAX_STAGES + 2 * MAX_ASETS), bar_accempty = bar_accfull + 16;
@@ -137,6 +176,7 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); }
     for (int s = 0; s < MAX_ASETS; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, EPI_THREADS); }
+    for (int s = 0; s < SCHED_DEPTH; ++s) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, SCHED_CONSUMERS); }
     fence_barrier_init();
   }
   if (warp == EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
@@ -146,7 +186,7 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long nworks = a.ngroups * a.NB;
+  const int ngroups = (int)a.ngroups, nworks = ngroups * a.NB;
   const int rows_h = a.ipt == 1 ? 18 : 20;                  // halo rows of a patch
   const uint32_t slab_bytes = (uint32_t)(rows_h * HC * 16); // K-direction stride between core matrices (LBO)
   const uint32_t S = (uint32_t)a.stages, AS = (uint32_t)a.asets, NA = (uint32_t)a.nacc;
@@ -185,10 +225,11 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
         }
       }
     };
-    uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++it) {
-      const int nb = (int)(w / a.ngroups);
-      const long long group = w - (long long)nb * a.ngroups;
+    for (uint32_t it = 0;; ++it) {
+      const int w = sched_consume(it, s_ring, bar_sfull, bar_sempty);
+      if (w >= nworks) break;
+      const int nb = w / ngroups;
+      const long long group = w - nb * ngroups;
       const uint32_t set = it % NA;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
@@ -272,13 +313,12 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
     const uint32_t set16 = (uint32_t)(a.TM * SLOT_BYTES) >> 4, stage16 = (uint32_t)stage_bytes >> 4, tap16 = (uint32_t)tap_bytes >> 4, lo_of_hi = 2u * (uint32_t)a.Nt;
     const uint32_t row16 = (uint32_t)(a.ipt * HC);            // one image row of the patch, in 16-byte units
     auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-    uint32_t ss = 0, a_ph = 0, s = 0, b_ph = 0, set = 0, acc_ph = 0, w_it = 0;
-    long long group = blockIdx.x % a.ngroups;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++w_it) {
-      const long long left = a.ntiles - group * a.TM;
+    uint32_t ss = 0, a_ph = 0, s = 0, b_ph = 0, set = 0, acc_ph = 0;
+    for (uint32_t w_it = 0;; ++w_it) {
+      const int w = sched_consume(w_it, s_ring, bar_sfull, bar_sempty);
+      if (w >= nworks) break;
+      const long long left = a.ntiles - (long long)(w % ngroups) * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
-      group += gridDim.x;
-      while (group >= a.ngroups) group -= a.ngroups;
       if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, acc_ph ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + set * (uint32_t)(a.TM * a.Nt);
@@ -334,8 +374,10 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
     const uint32_t box_bytes = 2u * slab_bytes;
     const uint32_t a_s = smem_u32(a_base);
     uint32_t ss = 0, ph = 0, it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
-      const long long group = w % a.ngroups;
+    for (uint32_t k = 0;; ++k) {
+      const int w = sched_produce(k, s_ring, bar_sfull, bar_sempty, a.sched);
+      if (w >= nworks) break;
+      const long long group = w % ngroups;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
       int cx[MAX_TM], cy[MAX_TM], cn[MAX_TM];               // tile coordinates: once per work item
@@ -375,14 +417,17 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
         if (++ss == AS) { ss = 0; ph ^= 1u; }
       }
     }
+    sched_retire(a.sched);
   } else {
     // =========================== weight producer ======================================================================
     const uint32_t b_s = smem_u32(b_base);
     const uint32_t nbytes = (a.dbg & 4) ? 16u : (uint32_t)stage_bytes;
     const int per_work = a.nchunks * 9 / a.tps;
     uint32_t s = 0, ph = 0, it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
-      const int nb = (int)(w / a.ngroups);
+    for (uint32_t k = 0;; ++k) {
+      const int w = sched_consume(k, s_ring, bar_sfull, bar_sempty);
+      if (w >= nworks) break;
+      const int nb = w / ngroups;
       const unsigned char *wsrc = a.wp + (size_t)nb * per_work * stage_bytes;
       for (int j = 0; j < per_work; ++j, ++it, wsrc += stage_bytes) {
         if (it >= S) mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
@@ -459,6 +504,23 @@ static EncodeTiledFn encode_tiled() {
     return (EncodeTiledFn)p;
   }();
   return fn;
+}
+
+// device-resident {next, retired} counter pairs for the dynamic work distribution, handed out round-robin per launch;
+// a pair re-arms itself when its launch retires, so only > 64 launches in flight at once could ever share one
+static unsigned int *sched_pair() {
+  constexpr int DEVICES = 64, PAIRS = 64;
+  static unsigned int *pool[DEVICES] = {};
+  static unsigned int next[DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= DEVICES) return nullptr;
+  if (pool[dev] == nullptr) {
+    unsigned int *p = nullptr;
+    if (cudaMalloc(&p, PAIRS * 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(p, 0, PAIRS * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    pool[dev] = p;
+  }
+  return pool[dev] + 2 * (next[dev]++ % PAIRS);
 }
 
 // tensor map over one plane of a split-planar activation tensor; box = one tile's patch of one 16-channel chunk
@@ -568,6 +630,9 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_conv3x3: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;
+  MVP_REQUIRE(nworks < (1LL << 30), MVP_ERR_UNSUPPORTED, "tc_conv3x3: too many work items");
+  a.sched = tcc::sched_pair();
+  MVP_REQUIRE(a.sched != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv3x3: could not allocate the scheduler counters");
   long long grid = sm_count();              // persistent, one CTA per SM
   if (grid > nworks) grid = nworks;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;

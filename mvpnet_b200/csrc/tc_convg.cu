@@ -47,6 +47,7 @@ struct ConvGArgs {
   int TX, TY;
   long long ntiles, ngroups;
   int TM, nacc, astages, stages, tmem_cols;
+  unsigned int *sched;              // dynamic work distribution counters (tc_conv.cu)
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1)
@@ -61,7 +62,9 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
   unsigned char *b_base = a_base + (size_t)a.astages * a_stage;
   uint64_t *bars = reinterpret_cast<uint64_t *>(b_base + (size_t)a.stages * b_stage);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * G_MAX_STAGES + 4);
-  float *s_bias = reinterpret_cast<float *>(bars + 32);          // [Cout]
+  volatile int *s_ring = reinterpret_cast<volatile int *>(bars + 30);    // [SCHED_DEPTH] work indices
+  const uint32_t bar_sfull = smem_u32(bars + 32), bar_sempty = smem_u32(bars + 32 + SCHED_DEPTH);
+  float *s_bias = reinterpret_cast<float *>(bars + 48);          // [Cout]
   const uint32_t bar_bfull = smem_u32(bars), bar_bempty = bar_bfull + 8 * G_MAX_STAGES;
   const uint32_t bar_afull = bar_bempty + 8 * G_MAX_STAGES, bar_aempty = bar_afull + 8 * G_MAX_STAGES;
   const uint32_t bar_accfull = bar_aempty + 8 * G_MAX_STAGES, bar_accempty = bar_accfull + 16;
@@ -72,6 +75,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1);
     }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_accfull + 8 * s, 1); mbar_init(bar_accempty + 8 * s, G_EPI_THREADS); }
+    for (int s = 0; s < SCHED_DEPTH; ++s) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 2 + G_EPI_THREADS / 32); }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
@@ -81,7 +85,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long nworks = a.ngroups * a.NB;
+  const int ngroups = (int)a.ngroups, nworks = ngroups * a.NB;
   const uint32_t S = (uint32_t)a.stages, AS = (uint32_t)a.astages, NA = (uint32_t)a.nacc;
   const int per_img = a.TX * a.TY;
   const int iters = a.nchunks * a.ntaps;                         // K-loop length of one work item
@@ -93,10 +97,11 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     const int C8o = a.Cout >> 3, out_pair = a.Ho <= 8;
     const size_t slab_stride = (size_t)a.Ho * a.Wo * 8 * (out_pair ? 2 : 1);
     const int blocks_per_parity = a.shuffle ? a.Cout / a.Nt : 0;
-    uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++it) {
-      const int nb = (int)(w / a.ngroups);
-      const long long group = w - (long long)nb * a.ngroups;
+    for (uint32_t it = 0;; ++it) {
+      const int w = sched_consume(it, s_ring, bar_sfull, bar_sempty);
+      if (w >= nworks) break;
+      const int nb = w / ngroups;
+      const long long group = w - nb * ngroups;
       const uint32_t set = it % NA;
       int py = 0, px = 0, co0 = nb * a.Nt;
       if (a.shuffle) { const int par = nb / blocks_per_parity; py = par >> 1; px = par & 1; co0 = (nb - par * blocks_per_parity) * a.Nt; }
@@ -152,9 +157,11 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     const uint64_t adesc0 = make_desc(0, 2048, 128), bdesc0 = make_desc(0, (uint32_t)a.Nt * 16u, 128);
     const uint32_t b_piece = 64u * (uint32_t)a.Nt, b_half = b_piece >> 1;   // one 16-channel piece: hi | lo
     const int ksteps = a.KC >> 4;
-    uint32_t a_it = 0, w_it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x, ++w_it) {
-      const long long group = w % a.ngroups;
+    uint32_t a_it = 0;
+    for (uint32_t w_it = 0;; ++w_it) {
+      const int w = sched_consume(w_it, s_ring, bar_sfull, bar_sempty);
+      if (w >= nworks) break;
+      const long long group = w % ngroups;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
       const uint32_t set = w_it % NA;
@@ -190,8 +197,10 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     const uint32_t a_s = smem_u32(a_base);
     const int C8 = a.Cin >> 3, kslabs = a.KC >> 3;
     uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
-      const long long group = w % a.ngroups;
+    for (uint32_t k = 0;; ++k) {
+      const int w = sched_produce(k, s_ring, bar_sfull, bar_sempty, a.sched);
+      if (w >= nworks) break;
+      const long long group = w % ngroups;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
       for (int c = 0; c < a.nchunks; ++c) {
@@ -218,14 +227,17 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
         }
       }
     }
+    sched_retire(a.sched);
   } else {
     // =========================== weight producer: KC/16 pieces per stage ============================================
     const uint32_t b_s = smem_u32(b_base);
     const uint32_t b_piece = 64u * (uint32_t)a.Nt;
     const int ks = a.KC >> 4, nch16 = a.Cin >> 4;
     uint32_t it = 0;
-    for (long long w = blockIdx.x; w < nworks; w += gridDim.x) {
-      const int nb = (int)(w / a.ngroups);
+    for (uint32_t k = 0;; ++k) {
+      const int w = sched_consume(k, s_ring, bar_sfull, bar_sempty);
+      if (w >= nworks) break;
+      const int nb = w / ngroups;
       const unsigned char *wsrc = a.wp + (size_t)nb * nch16 * a.ntaps * b_piece;
       for (int c = 0; c < a.nchunks; ++c) {
         for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
@@ -389,6 +401,9 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_convg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_conv_general: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;
+  MVP_REQUIRE(nworks < (1LL << 30), MVP_ERR_UNSUPPORTED, "tc_conv_general: too many work items");
+  a.sched = tcc::sched_pair();
+  MVP_REQUIRE(a.sched != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv_general: could not allocate the scheduler counters");
   long long grid = sm_count();
   if (grid > nworks) grid = nworks;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
