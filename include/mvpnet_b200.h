@@ -243,7 +243,7 @@ int mvp_merge_planar(const void *planar, int64_t N, int64_t H, int64_t W, int64_
  *           and, with mvp_unfold_stem, the 7x7 stem as seven row taps.
  *   mode 1  2x2 / stride-2 transposed convolution (unet_resnet34.py:31-60 deconv*): ntaps = 1, tap (0,0),
  *           Ho = 2 Hi, Wo = 2 Wi; GEMM column (2*ky + kx) * Cout + co.
- * Weights: [G/Nt][Cin/16][tap][hi|lo][2][Nt][8] bf16 with G = Cout (mode 0) or 4*Cout (mode 1), Nt = min(Cout, 256).
+ * Weights: [G/Nt][Cin/16][tap][hi|lo][2][Nt][8] bf16 with G = Cout (mode 0) or 4*Cout (mode 1), Nt = min(G, 256).
  * mvp_unfold_stem: fp32 NCHW 3-channel image -> split-planar (N, H, W, 32): channel kx*3 + c = image[n, c, y, x+kx-3].
  * mvp_maxpool3x3s2_planar: 3x3 / stride 2 / pad 1 max-pool, split-planar in and out ((H-1)/2+1 x (W-1)/2+1). */
 int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_t Hi, int64_t Wi, int mode, int stride, int ntaps,

@@ -609,6 +609,8 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
     a.dbg = e ? atoi(e) : 0;
     const char *st = getenv("MVPNET_B200_CONV_STAGES");
     if (st && atoi(st) >= 2 && atoi(st) <= tcc::MAX_STAGES) a.stages = atoi(st);
+    const char *as = getenv("MVPNET_B200_CONV_ASETS");
+    if (as && atoi(as) >= 2 && atoi(as) <= tcc::MAX_ASETS) a.asets = atoi(as);
     const char *tp = getenv("MVPNET_B200_CONV_TPS");
     if (tp && (atoi(tp) == 1 || atoi(tp) == 3 || atoi(tp) == 9)) a.tps = atoi(tp);
     const char *tm = getenv("MVPNET_B200_CONV_TM");

@@ -36,6 +36,7 @@ struct ConvGArgs {
   int ntaps;
   int tdy[G_MAX_TAPS], tdx[G_MAX_TAPS];
   int in_pair;                      // input planes are pair-interleaved (Hi <= 8)
+  int merged;                       // stride 1: the tensor maps fold (channel-in-slab, x) into one dimension (128-byte box rows)
   int shuffle;                      // transposed 2x2/s2: output block nb -> parity, out pixel = 2 * row pixel + parity
   const unsigned char *wp;          // [nb][Cin/16][tap][hi|lo][2][Nt][8] bf16 (the layout of tc_conv.cu with `ntaps` taps)
   const float *bias;                // [Cout]
@@ -96,15 +97,12 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int C8o = a.Cout >> 3, out_pair = a.Ho <= 8;
     const size_t slab_stride = (size_t)a.Ho * a.Wo * 8 * (out_pair ? 2 : 1);
-    const int blocks_per_parity = a.shuffle ? a.Cout / a.Nt : 0;
     for (uint32_t it = 0;; ++it) {
       const int w = sched_consume(it, s_ring, bar_sfull, bar_sempty);
       if (w >= nworks) break;
       const int nb = w / ngroups;
       const long long group = w - nb * ngroups;
       const uint32_t set = it % NA;
-      int py = 0, px = 0, co0 = nb * a.Nt;
-      if (a.shuffle) { const int par = nb / blocks_per_parity; py = par >> 1; px = par & 1; co0 = (nb - par * blocks_per_parity) * a.Nt; }
       mbar_wait(bar_accfull + 8 * set, (it / NA) & 1u);
       tc_fence_after();
       for (int t = 0; t < a.TM; ++t) {
@@ -113,8 +111,6 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
         const int n = (int)(tile / per_img), r = (int)(tile - (long long)n * per_img);
         const int yr = (r / a.TX) * 16 + g, xr = (r % a.TX) * 8 + xx;
         const bool ok = yr < a.Hr && xr < a.Wr;
-        const int yo = a.shuffle ? 2 * yr + py : yr, xo = a.shuffle ? 2 * xr + px : xr;
-        const size_t pbase = ok ? planar_off(n, co0 >> 3, yo, xo, C8o, a.Ho, a.Wo, out_pair) : 0;
         const uint32_t t_acc = t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
         uint32_t rn[16];
         tmem_ld16_issue(t_acc, rn);
@@ -124,7 +120,12 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
           if (c + 16 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 16), rn);
-          const float4 *bp = reinterpret_cast<const float4 *>(s_bias + co0 + c);
+          // GEMM column -> (parity, output channel): a 16-column chunk never straddles a parity (Cout % 16 == 0)
+          const int col = nb * a.Nt + c;
+          const int par = a.shuffle ? col / a.Cout : 0, co = a.shuffle ? col - par * a.Cout : col;
+          const int yo = a.shuffle ? 2 * yr + (par >> 1) : yr, xo = a.shuffle ? 2 * xr + (par & 1) : xr;
+          const size_t pbase = ok ? planar_off(n, co >> 3, yo, xo, C8o, a.Ho, a.Wo, out_pair) : 0;
+          const float4 *bp = reinterpret_cast<const float4 *>(s_bias + co);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 bq = bp[q];
@@ -140,7 +141,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
               uint32_t h[4], l[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) split_pair(v[8 * s + 2 * q], v[8 * s + 2 * q + 1], h[q], l[q]);
-              const size_t o = pbase + (size_t)((c >> 3) + s) * slab_stride;
+              const size_t o = pbase + (size_t)s * slab_stride;
               *reinterpret_cast<uint4 *>(a.out_p + o) = make_uint4(h[0], h[1], h[2], h[3]);
               *reinterpret_cast<uint4 *>(a.out_p + a.plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
             }
@@ -152,37 +153,45 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     }
   } else if (warp == 4) {
     // =========================== MMA issuer (whole warp walks, one elected lane issues) ==============================
+    // running ring positions / phases and 32-bit descriptor arithmetic only: see tc_conv.cu
     const uint32_t idesc = make_idesc(128, a.Nt);
-    const uint32_t a_s = smem_u32(a_base), b_s = smem_u32(b_base);
     const uint64_t adesc0 = make_desc(0, 2048, 128), bdesc0 = make_desc(0, (uint32_t)a.Nt * 16u, 128);
-    const uint32_t b_piece = 64u * (uint32_t)a.Nt, b_half = b_piece >> 1;   // one 16-channel piece: hi | lo
+    const uint32_t a_lo0 = (uint32_t)adesc0 + (smem_u32(a_base) >> 4), a_hi32 = (uint32_t)(adesc0 >> 32);
+    const uint32_t b_lo0 = (uint32_t)bdesc0 + (smem_u32(b_base) >> 4), b_hi32 = (uint32_t)(bdesc0 >> 32);
+    const uint32_t a_stage16 = a_stage >> 4, a_tile16 = a_tile >> 4, a_half16 = a_half >> 4, b_stage16 = b_stage >> 4;
+    const uint32_t b_piece16 = 4u * (uint32_t)a.Nt, b_half16 = b_piece16 >> 1;   // one 16-channel piece: hi | lo
     const int ksteps = a.KC >> 4;
-    uint32_t a_it = 0;
+    auto desc64 = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+    uint32_t sa = 0, a_ph = 0, sb = 0, b_ph = 0, set = 0, acc_ph = 0;
     for (uint32_t w_it = 0;; ++w_it) {
       const int w = sched_consume(w_it, s_ring, bar_sfull, bar_sempty);
       if (w >= nworks) break;
-      const long long group = w % ngroups;
-      const long long left = a.ntiles - group * a.TM;
+      const long long left = a.ntiles - (long long)(w % ngroups) * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
-      const uint32_t set = w_it % NA;
-      if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, ((w_it / NA) - 1u) & 1u);
+      if (w_it >= NA) mbar_wait(bar_accempty + 8 * set, acc_ph ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + set * (uint32_t)(a.TM * a.Nt);
-      for (int i = 0; i < iters; ++i, ++a_it) {
-        const uint32_t sa = a_it % AS, sb = a_it % S;
-        mbar_wait(bar_afull + 8 * sa, (a_it / AS) & 1u);
-        mbar_wait(bar_bfull + 8 * sb, (a_it / S) & 1u);
-        const uint32_t a_st = a_s + sa * a_stage, b_hi = b_s + sb * b_stage;
+      uint32_t first = 0u;
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(bar_afull + 8 * sa, a_ph);
+        mbar_wait(bar_bfull + 8 * sb, b_ph);
+        const uint32_t a_lo = a_lo0 + sa * a_stage16, b_lo = b_lo0 + sb * b_stage16;
         if (elect_one()) {
-          for (int t = 0; t < nt; ++t) {
-            const uint32_t d = d0 + (uint32_t)(t * a.Nt);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t ah_a = a_st + (uint32_t)t * a_tile + (uint32_t)k * 4096u, bh_a = b_hi + (uint32_t)k * b_piece;
-              const uint64_t ah = adesc0 | (uint64_t)((ah_a >> 4) & 0x3fffu), al = adesc0 | (uint64_t)(((ah_a + a_half) >> 4) & 0x3fffu);
-              const uint64_t bh = bdesc0 | (uint64_t)((bh_a >> 4) & 0x3fffu), bl = bdesc0 | (uint64_t)(((bh_a + b_half) >> 4) & 0x3fffu);
-              umma_bf16(d, ah, bh, idesc, (i == 0 && k == 0) ? 0u : 1u);
-              umma_bf16(d, ah, bl, idesc, 1u);
-              umma_bf16(d, al, bh, idesc, 1u);
+#pragma unroll
+          for (int t = 0; t < MAX_TM; ++t) {
+            if (t < nt) {
+              const uint32_t d = d0 + (uint32_t)(t * a.Nt);
+              uint32_t al = a_lo + (uint32_t)t * a_tile16, bl = b_lo, acc = first;
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t ah = desc64(al, a_hi32), alo = desc64(al + a_half16, a_hi32);
+                const uint64_t bh = desc64(bl, b_hi32), blo = desc64(bl + b_half16, b_hi32);
+                umma_bf16(d, ah, bh, idesc, acc);
+                umma_bf16(d, ah, blo, idesc, 1u);
+                umma_bf16(d, alo, bh, idesc, 1u);
+                al += 256u;                  // two 2048-byte slabs
+                bl += b_piece16;
+                acc = 1u;
+              }
             }
           }
           umma_commit(bar_bempty + 8 * sb);
@@ -190,40 +199,61 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
           if (i == iters - 1) umma_commit(bar_accfull + 8 * set);
         }
         __syncwarp();
+        first = 1u;
+        if (++sa == AS) { sa = 0; a_ph ^= 1u; }
+        if (++sb == S) { sb = 0; b_ph ^= 1u; }
       }
+      if (++set == NA) { set = 0; acc_ph ^= 1u; }
     }
   } else if (warp == 5) {
     // =========================== input producer: one TMA box per (tile, chunk, tap, plane) ===========================
     const uint32_t a_s = smem_u32(a_base);
     const int C8 = a.Cin >> 3, kslabs = a.KC >> 3;
-    uint32_t it = 0;
+    const int xs = a.merged ? 8 : 1;                        // merged maps address x in elements of the (8 * W) dimension
+    uint32_t sa = 0, ph = 0, it = 0;
     for (uint32_t k = 0;; ++k) {
       const int w = sched_produce(k, s_ring, bar_sfull, bar_sempty, a.sched);
       if (w >= nworks) break;
-      const long long group = w % ngroups;
-      const long long left = a.ntiles - group * a.TM;
+      const int group = w % ngroups;
+      const long long left = a.ntiles - (long long)group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
+      int cx[MAX_TM], cy[MAX_TM], cn[MAX_TM];               // tile origins in the input grid: once per work item
+#pragma unroll
+      for (int t = 0; t < MAX_TM; ++t) {
+        const long long tile = (long long)group * a.TM + (t < nt ? t : 0);
+        const int n = (int)(tile / per_img), r = (int)(tile - (long long)n * per_img);
+        cy[t] = (r / a.TX) * 16 * a.stride; cx[t] = (r % a.TX) * 8 * a.stride; cn[t] = n;
+      }
       for (int c = 0; c < a.nchunks; ++c) {
         for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
-          const uint32_t sa = it % AS;
-          if (it >= AS) mbar_wait(bar_aempty + 8 * sa, ((it / AS) - 1u) & 1u);
+          if (it >= AS) mbar_wait(bar_aempty + 8 * sa, ph ^ 1u);
+          const uint32_t bar = bar_afull + 8 * sa, dst0 = a_s + sa * a_stage;
+          const int dy = a.tdy[tap], dx = a.tdx[tap];
           if (elect_one()) {
-            mbar_expect_tx(bar_afull + 8 * sa, (uint32_t)nt * a_tile);
-            for (int t = 0; t < nt; ++t) {
-              const long long tile = group * a.TM + t;
-              const int n = (int)(tile / per_img), r = (int)(tile - (long long)n * per_img);
-              const int y = (r / a.TX) * 16 * a.stride + a.tdy[tap], x = (r % a.TX) * 8 * a.stride + a.tdx[tap];
-              const uint32_t dst = a_s + sa * a_stage + (uint32_t)t * a_tile;
-              if (!a.in_pair) {            // dims (8, W, H, C8 * N)
-                tma_load_4d(dst, &a.mh, 0, x, y, n * C8 + c * kslabs, bar_afull + 8 * sa);
-                tma_load_4d(dst + a_half, &a.ml, 0, x, y, n * C8 + c * kslabs, bar_afull + 8 * sa);
-              } else {                     // dims (8, W, 2, H, C8 * N/2)
-                tma_load_5d(dst, &a.mh, 0, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar_afull + 8 * sa);
-                tma_load_5d(dst + a_half, &a.ml, 0, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar_afull + 8 * sa);
+            mbar_expect_tx(bar, (uint32_t)nt * a_tile);
+#pragma unroll
+            for (int t = 0; t < MAX_TM; ++t) {
+              if (t < nt) {
+                const uint32_t dst = dst0 + (uint32_t)t * a_tile;
+                const int x = (cx[t] + dx) * xs, y = cy[t] + dy, n = cn[t];
+                if (a.merged && !a.in_pair) {         // dims (8 * W, H, C8 * N)
+                  tma_load_3d(dst, &a.mh, x, y, n * C8 + c * kslabs, bar);
+                  tma_load_3d(dst + a_half, &a.ml, x, y, n * C8 + c * kslabs, bar);
+                } else if (a.merged) {                // dims (8 * W, 2, H, C8 * N/2)
+                  tma_load_4d(dst, &a.mh, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar);
+                  tma_load_4d(dst + a_half, &a.ml, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar);
+                } else if (!a.in_pair) {              // dims (8, W, H, C8 * N), traversal stride on W and H
+                  tma_load_4d(dst, &a.mh, 0, x, y, n * C8 + c * kslabs, bar);
+                  tma_load_4d(dst + a_half, &a.ml, 0, x, y, n * C8 + c * kslabs, bar);
+                } else {                              // dims (8, W, 2, H, C8 * N/2)
+                  tma_load_5d(dst, &a.mh, 0, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar);
+                  tma_load_5d(dst + a_half, &a.ml, 0, x, n & 1, y, (n >> 1) * C8 + c * kslabs, bar);
+                }
               }
             }
           }
           __syncwarp();
+          if (++sa == AS) { sa = 0; ph ^= 1u; }
         }
       }
     }
@@ -233,7 +263,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     const uint32_t b_s = smem_u32(b_base);
     const uint32_t b_piece = 64u * (uint32_t)a.Nt;
     const int ks = a.KC >> 4, nch16 = a.Cin >> 4;
-    uint32_t it = 0;
+    uint32_t s = 0, ph = 0, it = 0;
     for (uint32_t k = 0;; ++k) {
       const int w = sched_consume(k, s_ring, bar_sfull, bar_sempty);
       if (w >= nworks) break;
@@ -241,14 +271,14 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       const unsigned char *wsrc = a.wp + (size_t)nb * nch16 * a.ntaps * b_piece;
       for (int c = 0; c < a.nchunks; ++c) {
         for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
-          const uint32_t s = it % S;
-          if (it >= S) mbar_wait(bar_bempty + 8 * s, ((it / S) - 1u) & 1u);
+          if (it >= S) mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
           if (elect_one()) {
             mbar_expect_tx(bar_bfull + 8 * s, b_stage);
-            for (int k = 0; k < ks; ++k)
-              bulk_g2s(b_s + s * b_stage + (uint32_t)k * b_piece, wsrc + ((size_t)(c * ks + k) * a.ntaps + tap) * b_piece, b_piece, bar_bfull + 8 * s);
+            for (int kk = 0; kk < ks; ++kk)
+              bulk_g2s(b_s + s * b_stage + (uint32_t)kk * b_piece, wsrc + ((size_t)(c * ks + kk) * a.ntaps + tap) * b_piece, b_piece, bar_bfull + 8 * s);
           }
           __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -322,23 +352,33 @@ maxpool_planar_kernel(const __nv_bfloat16 *__restrict__ src, long long plane_in,
   }
 }
 
-// tensor map over one plane with unmerged (channel-in-slab, x, [pair,] y, slab) dimensions and a traversal stride
+// tensor map over one plane; box = the 16 x 8 pixels x `kslabs` slabs of one tile.  stride 1: (channel-in-slab, x) folded
+// into one dimension, so a box row is one 128-byte request; stride 2: unmerged dimensions with a traversal stride.
 static int make_plane_map_g(CUtensorMap *m, const void *plane, int64_t N, int64_t H, int64_t W, int64_t C, int pair, int stride, int kslabs) {
   EncodeTiledFn enc = encode_tiled();
   MVP_REQUIRE(enc != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv: cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t C8 = (cuuint64_t)(C / 8);
-  const cuuint32_t st = (cuuint32_t)stride;
+  const cuuint64_t C8 = (cuuint64_t)(C / 8), NP = (cuuint64_t)((N + 1) / 2);
+  const cuuint32_t st = (cuuint32_t)stride, ks = (cuuint32_t)kslabs;
+  const cuuint64_t w16 = (cuuint64_t)W * 16, hw16 = (cuuint64_t)H * W * 16;
   CUresult r;
-  if (!pair) {
-    const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, C8 * (cuuint64_t)N};
-    const cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-    const cuuint32_t box[4] = {8, 8 * st, 16 * st, (cuuint32_t)kslabs}, es[4] = {1, st, st, 1};
+  if (stride == 1 && !pair) {
+    const cuuint64_t dims[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, C8 * (cuuint64_t)N}, strides[2] = {w16, hw16};
+    const cuuint32_t box[3] = {64, 16, ks}, es[3] = {1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (stride == 1) {
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, 2, (cuuint64_t)H, C8 * NP}, strides[3] = {w16, 2 * w16, 2 * hw16};
+    const cuuint32_t box[4] = {64, 1, 16, ks}, es[4] = {1, 1, 1, 1};
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (!pair) {
+    const cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, C8 * (cuuint64_t)N}, strides[3] = {16, w16, hw16};
+    const cuuint32_t box[4] = {8, 8 * st, 16 * st, ks}, es[4] = {1, st, st, 1};
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
-    const cuuint64_t dims[5] = {8, (cuuint64_t)W, 2, (cuuint64_t)H, C8 * (cuuint64_t)((N + 1) / 2)};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)2 * W * 16, (cuuint64_t)H * 2 * W * 16};
-    const cuuint32_t box[5] = {8, 8 * st, 1, 16 * st, (cuuint32_t)kslabs}, es[5] = {1, st, 1, st, 1};
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W, 2, (cuuint64_t)H, C8 * NP}, strides[4] = {16, w16, 2 * w16, 2 * hw16};
+    const cuuint32_t box[5] = {8, 8 * st, 1, 16 * st, ks}, es[5] = {1, st, 1, st, 1};
     r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
@@ -363,6 +403,8 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
               "tc_conv_general: bad mode / stride / taps");
   MVP_REQUIRE(mode == 0 || (ntaps == 1 && stride == 1 && Ho == 2 * Hi && Wo == 2 * Wi), MVP_ERR_INVALID_ARG,
               "tc_conv_general: a transposed convolution has one tap and doubles the grid");
+  MVP_REQUIRE(mode == 0 || 4 * Cout <= 256 || (4 * Cout) % 256 == 0, MVP_ERR_UNSUPPORTED,
+              "tc_conv_general: 4 x Cout of a transposed convolution must be <= 256 or a multiple of 256");
   MVP_REQUIRE(N * Ho * Wo < (1LL << 31) && N * Hi * Wi < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv_general: more than 2^31 pixels");
   if (N == 0) return 0;
   MVP_REQUIRE(x && w_packed && bias && out_planar, MVP_ERR_NULL, "tc_conv_general: null pointer");
@@ -374,8 +416,10 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   a.in_pair = Hi <= 8 ? 1 : 0;
   const int64_t Np_in = a.in_pair ? (N + 1) / 2 * 2 : N, Np_out = Ho <= 8 ? (N + 1) / 2 * 2 : N;
   a.wp = (const unsigned char *)w_packed; a.bias = bias; a.out_p = (__nv_bfloat16 *)out_planar; a.plane_out = Np_out * Cout * Ho * Wo;
-  a.relu = relu; a.Cout = (int)Cout; a.Nt = Cout <= 256 ? (int)Cout : 256;
-  a.NB = (mode ? 4 : 1) * (a.Cout / a.Nt);
+  a.relu = relu; a.Cout = (int)Cout;
+  const int64_t G = mode ? 4 * Cout : Cout;                  // GEMM columns: a transposed convolution carries its 4 parities side by side
+  a.Nt = G <= 256 ? (int)G : 256; a.NB = (int)(G / a.Nt);
+  a.merged = stride == 1 ? 1 : 0;
   a.TX = (a.Wr + 7) / 8; a.TY = (a.Hr + 15) / 16;
   a.ntiles = N * a.TX * a.TY;
   a.TM = a.Nt <= 64 ? 4 : 2;
@@ -384,9 +428,10 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
   a.tmem_cols = 32;
   while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
-  // channels per stage: a stage holds TM tiles x KC channels x 512 B (hi + lo), kept at <= 32 KB
-  a.KC = 64 / a.TM;
-  while (a.KC > 16 && Cin % a.KC != 0) a.KC >>= 1;
+  // channels per stage: as many as keep three input stages (TM tiles x KC channels x 512 B) + three weight stages
+  // (KC x Nt x 4 B) in shared memory — every stage costs the issuer a barrier round trip
+  a.KC = 64;
+  while (a.KC > 16 && (Cin % a.KC != 0 || 3 * ((size_t)a.TM * a.KC * 512 + (size_t)a.KC * a.Nt * 4) + 1024 + Cout * 4 > tc::SMEM_CAP)) a.KC >>= 1;
   a.nchunks = (int)(Cin / a.KC);
   if (int rc = tcc::make_plane_map_g(&a.mh, x, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
   if (int rc = tcc::make_plane_map_g(&a.ml, (const __nv_bfloat16 *)x + Np_in * Cin * Hi * Wi, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;

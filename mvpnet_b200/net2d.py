@@ -73,7 +73,8 @@ def pack_deconv2x2(weight, bias):
     cin, cout = weight.shape[0], weight.shape[1]
     assert weight.shape[2:] == (2, 2)
     wg = weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1)
-    return pack_taps(wg, _nt(cout)), bias.float().contiguous()
+    assert cout % 16 == 0 and (4 * cout <= 256 or (4 * cout) % 256 == 0)
+    return pack_taps(wg, min(4 * cout, 256)), bias.float().contiguous()
 
 
 def pack_stem7x7(weight, bias):

@@ -35,8 +35,8 @@ def emulated_general(x, mode, stride, dy, dx, ho, wo, packed, bias, relu):
     """x (N, Hi, Wi, Cin) fp32; the documented semantics of mvp_tc_conv_general, tap by tap."""
     n, hi_, wi_, cin = x.shape
     cout = bias.numel()
-    nt = cout if cout <= 256 else 256
     g = 4 * cout if mode else cout
+    nt = g if g <= 256 else 256
     whi, wlo = unpack_taps(packed, cin, g, len(dy), nt)
     wg = (whi + wlo).double()
     xd = x.double()
