@@ -7,7 +7,8 @@
 
 A step = one pass of the hot path over one batch of synthetic chunks per GPU (BASELINE config 4's
 per-rank shard: 32 chunks x 8192 points x 5 views of 160x120): depth unprojection + 2D->3D 3-NN,
-UNet-ResNet34 on the views, FeatureAggregation, PN2SSG, and (N > 1) one NCCL all-gather of the logits.
+UNet-ResNet34 on the views (this package's tcgen05 convolutions), FeatureAggregation, PN2SSG, and (N > 1) one NCCL
+all-gather of the logits.
 
   value  chunks/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
   e2e    chunks/s through the public API from pinned HOST buffers: H2D of the step's inputs and the
@@ -138,16 +139,28 @@ def algorithmic_bytes_per_chunk():
     return out
 
 
+# multiply-adds of the UNet-ResNet34 per 128x160 (padded) view, by kernel family (counted layer by layer from
+# unet_resnet34.py:9-125): 3x3/stride-1 convolutions 8114 M, the other layers (7x7 stem, three stride-2 3x3, three 1x1
+# down-samples, four 2x2 transposed) 715 M
+NET2D_MMAC_PER_VIEW = {'net_2d/conv3x3': 8114.0, 'net_2d/conv_general': 715.0}
+
+
 def algorithmic_gflop_per_chunk():
-    """MLP-chain flops per chunk."""
-    return {'feature_aggregation': 0.617, 'set_abstraction1': 0.684, 'set_abstraction2': 0.543, 'set_abstraction3': 0.540,
+    """Contraction flops per chunk: MLP chains and the 2D network's convolutions."""
+    conv = {k: 2 * v * NUM_VIEWS / 1e3 for k, v in NET2D_MMAC_PER_VIEW.items()}
+    conv['net_2d'] = sum(conv.values())
+    return {**conv, 'feature_aggregation': 0.617, 'set_abstraction1': 0.684, 'set_abstraction2': 0.543, 'set_abstraction3': 0.540,
             'set_abstraction4': 0.538, 'feature_propagation1': 0.067, 'feature_propagation2': 0.168,
             'feature_propagation3': 0.470, 'feature_propagation4': 0.805 + 0.310}
 
 
 def stage_bound(name):
     if name == 'net_2d':
-        return 'cuDNN (out of scope)'
+        return 'tensor (tcgen05 convolutions, bf16 hi/lo x3; sum of the net_2d/* stages)'
+    if name in ('net_2d/conv3x3', 'net_2d/conv_general'):
+        return 'tensor (tcgen05, bf16 hi/lo x3)'
+    if name == 'net_2d/pool_unfold':
+        return 'hbm'
     if name in ('unproject',):
         return 'hbm'
     if name == 'feature_aggregation':
@@ -161,8 +174,10 @@ def stage_bound(name):
     return 'fp32 CUDA-core compute (exhaustive search)'
 
 
-# one launch per stage except the k-NN grid build (bbox, count, scan, scatter, query): kernels of this package per step
-KERNELS_PER_STEP = 1 + 5 + 1 + 4 * 5
+# kernels of this package per step (counted in profiles/r1_launches_*: unproject 1, pixel k-NN grid 5, FPS 4,
+# ball query 4 + grid 5, 3-NN 4 + grid 5, fused FA/SA/FP 9, 2D network: 3x3 convolutions 33, other layers 11,
+# stem unfold 1, max-pool 1); ATen adds 11 small copies / gathers
+KERNELS_PER_STEP = 83
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed ncu capture (profiles/r1_ncu_*.md)
 NCU_TRAFFIC_MB = {}
 
@@ -172,6 +187,14 @@ def tensor_peak():
     if os.path.exists(path):
         return float(json.load(open(path)).get('bf16_tflops', 1590.0))
     return 1590.0
+
+
+def tensor_peak_sustained():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p.get('bf16_tflops_sustained', p.get('bf16_tflops', 1400.0)))
+    return 1400.0
 
 
 def peaks():
@@ -313,7 +336,7 @@ def main():
               'chunks_per_gpu': args.chunks_per_gpu, 'global_chunks': args.chunks_per_gpu * world,
               'parallelism': 'chunk-sharded x%d, replicated weights' % world,
               'l2_policy': 'no flush: per-step working set (~0.8 GB of images/feature maps per GPU) exceeds the 126 MB L2',
-              'net_2d_math': 'tf32' if args.tf32_2d else 'fp32 (cuDNN, TF32 off)'}
+              'net_2d_math': 'tcgen05 convolutions of this package, bf16 hi/lo x 3 products, fp32 accumulate (MVPNET_B200_NET2D=cudnn: cuDNN fp32)'}
 
     if args.impl == 'reference':
         if rank != 0:
@@ -428,10 +451,12 @@ def main():
     # per-stage device time of this package's kernels (events on the launching stream), no overlap
     stage_ms = {}
     with torch.no_grad(), engine.profile() as prof:
-        for _ in range(max(3, min(args.steps, 5))):
+        reps = max(3, min(args.steps, 5))
+        for _ in range(reps):
             hot_path(model, dev, overlap=False)
-        for k, v in prof.summary().items():
-            stage_ms[k] = float(np.median(v))
+        for k, v in prof.summary().items():          # stages launched several times per forward: per-forward sums
+            per_fwd = np.asarray(v, dtype=np.float64).reshape(reps, -1).sum(axis=1)
+            stage_ms[k] = float(np.median(per_fwd))
 
     if rank != 0:
         if world > 1:
@@ -447,7 +472,7 @@ def main():
     flops_pc = algorithmic_gflop_per_chunk()
     peak, peak_src = peaks()
     tpeak = tensor_peak()
-    mine = {k: v for k, v in stage_ms.items() if k != 'net_2d'}
+    mine = {k: v for k, v in stage_ms.items() if k != 'net_2d'}          # net_2d is the sum of its net_2d/* stages
     stages = {}
     for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1]):
         e = {'ms': round(v, 4), 'bound': stage_bound(k)}
@@ -463,20 +488,27 @@ def main():
         stages[k] = e
     # headline roofline: the dominant kernel of this package that is HBM- or tensor-bound by design (the k-NN searches
     # and FPS are CUDA-core-compute / serial-latency bound: their entries in `stages` carry times and bounds instead)
-    fused = [k for k in mine if k in flops_pc]
-    top = max(fused, key=mine.get)
+    fused = [k for k in mine if k in flops_pc and not k.startswith('net_2d')]
+    # headline roofline: the kernel family of this package that takes the most device time in the step
+    launches = {'net_2d/conv3x3': 33, 'net_2d/conv_general': 11}
+    top = max([k for k in mine if k in flops_pc and k != 'net_2d'], key=mine.get)
     t_fused = sum(mine[k] for k in fused)
     gf_fused = sum(flops_pc[k] for k in fused) * cpg
-    roof = {'kernel': top, 'bound': 'hbm' if top == 'feature_aggregation' else 'tensor', 'peak_source': peak_src,
-            'ms_per_launch': mine[top], 'traffic': NCU_TRAFFIC_MB.get(top),
-            'traffic_note': 'MB per launch, dram__bytes_read+write from profiles/ (ncu --set full)',
-            'note': 'algorithmic bytes/flops per launch = per-chunk figure (SURVEY 8d) x %d chunks per launch' % cpg}
+    n_launch = launches.get(top, 1)
+    roof = {'kernel': top + (' (tc_conv3x3_kernel, %d launches per step: every 3x3/stride-1 convolution of the UNet)' % n_launch if top == 'net_2d/conv3x3' else ''),
+            'bound': 'hbm' if top == 'feature_aggregation' else 'tensor', 'peak_source': peak_src,
+            'launches_per_step': n_launch, 'ms_per_launch': mine[top] / n_launch,
+            'traffic': NCU_TRAFFIC_MB.get(top),
+            'traffic_note': 'MB per launch (mean over the launches of the step), dram__bytes_read+write from profiles/ (ncu --set full)',
+            'note': 'algorithmic flops per launch = per-chunk figure x %d chunks per step / launches per step; time = CUDA events around every launch, summed per step' % cpg}
     if roof['bound'] == 'hbm':
         ach = bytes_pc[top] * cpg / (mine[top] / 1e3) / 1e9
         roof.update({'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak})
     else:
         ach = 3 * flops_pc[top] * cpg / mine[top]
-        roof.update({'achieved': ach, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': ach / tpeak,
+        sustained = tensor_peak_sustained()
+        roof.update({'achieved': ach, 'peak': sustained, 'unit': 'TFLOP/s', 'frac': ach / sustained,
+                     'peak_kind': 'bf16_tflops_sustained of MEASURED_PEAKS.json (kernels timed inside a long step); burst peak %.1f -> frac %.4f' % (tpeak, ach / tpeak),
                      'note2': 'issued bf16 tensor flops (3 products per useful MAC); useful fp32-equivalent = achieved / 3'})
     bq_group = mine.get('ball_query1', 0) + mine.get('set_abstraction1', 0)
     line = {'metric': METRIC, 'value': value, 'unit': 'chunks/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
@@ -494,7 +526,7 @@ def main():
                     'ms': round(bq_group, 4), 'GBps': round(20.93e6 * cpg / (bq_group / 1e3) / 1e9, 1) if bq_group else None,
                     'hbm_frac': round(20.93e6 * cpg / (bq_group / 1e3) / 1e9 / peak, 4) if bq_group else None}},
             'stages': stages,
-            'hot_path_ms_per_step_excl_net2d': sum(mine.values())}
+            'hot_path_ms_per_step_excl_net2d': sum(v for k, v in mine.items() if not k.startswith('net_2d'))}
     if world == 1:
         try:
             rk = reference_kernel_times(dev['points'])

@@ -223,11 +223,12 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
  * mvp_planar_elems() gives the bf16 element count of both planes; mvp_split_planar / mvp_merge_planar convert from /
  * to fp32 NHWC.  x2 may be NULL (C2 = 0): cat([up, skip]) without the copy.  residual (split-planar, Cout channels)
  * may be NULL.  The result is written split-planar (out_planar) and / or as fp32 NHWC (out_nhwc); at least one.
- * C1, C2, Cout multiples of 16 (Cout a multiple of 256 above 256).  Weights (BatchNorm folded by the caller) are
+ * C1, C2, Cout multiples of 16 (Cout a multiple of Nt above it).  Weights (BatchNorm folded by the caller) are
  * split the same way and stored in the kernel's operand order [Cout/Nt][Cin/16][tap = ky*3+kx][hi|lo][2][Nt][8],
- * Nt = min(Cout, 256), element (nb, c, tap, hl, k8, n, e) = W_hl[nb*Nt + n, c*16 + k8*8 + e, ky, kx]:
+ * Nt = mvp_tc_conv3x3_nt(Cout) (= min(Cout, 256)), element (nb, c, tap, hl, k8, n, e) = W_hl[nb*Nt + n, c*16 + k8*8 + e, ky, kx]:
  * mvp_tc_conv3x3_weight_bytes() bytes. */
 int64_t mvp_tc_conv3x3_weight_bytes(int64_t Cin, int64_t Cout);
+int64_t mvp_tc_conv3x3_nt(int64_t Cout);
 int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C);
 int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
                    const void *w_packed, const float *bias, int64_t Cout, const void *residual, int relu,

@@ -554,6 +554,15 @@ static int make_plane_map(CUtensorMap *m, const void *plane, int64_t N, int64_t 
 
 extern "C" int64_t mvp_tc_conv3x3_weight_bytes(int64_t Cin, int64_t Cout) { return Cin * Cout * 9 * 4; }
 
+// width of one block of output channels (GEMM N per accumulator) — part of the packed-weight layout.  256 = the widest
+// tcgen05 N: measured against 128 (twice as many, half as long work items, two accumulator sets) the wide layers run
+// 20 % slower at 128 (layer3 0.190 vs 0.152 ms) because every patch is then fetched twice as often.
+// MVPNET_B200_CONV3_NT overrides (experiments).
+extern "C" int64_t mvp_tc_conv3x3_nt(int64_t Cout) {
+  static const int64_t cap = [] { const char *e = getenv("MVPNET_B200_CONV3_NT"); const int64_t v = e ? atoll(e) : 0; return (v == 64 || v == 128 || v == 256) ? v : (int64_t)256; }();
+  return Cout <= cap ? Cout : cap;
+}
+
 // elements (bf16) of a split-planar tensor: both planes
 extern "C" int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C) {
   const int64_t n = H <= 8 ? (N + 1) / 2 * 2 : N;
@@ -566,8 +575,8 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   using namespace mvp;
   MVP_REQUIRE(N >= 0 && H > 0 && W > 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: bad sizes");
   MVP_REQUIRE(C1 > 0 && C1 % 16 == 0 && C2 >= 0 && C2 % 16 == 0, MVP_ERR_UNSUPPORTED, "tc_conv3x3: input channels must be multiples of 16");
-  MVP_REQUIRE(Cout > 0 && Cout % 16 == 0 && (Cout <= 256 || Cout % 256 == 0), MVP_ERR_UNSUPPORTED,
-              "tc_conv3x3: output channels must be a multiple of 16, and of 256 above 256");
+  MVP_REQUIRE(Cout > 0 && Cout % 16 == 0 && Cout % mvp_tc_conv3x3_nt(Cout) == 0, MVP_ERR_UNSUPPORTED,
+              "tc_conv3x3: output channels must be a multiple of 16, and of the block width mvp_tc_conv3x3_nt() above it");
   MVP_REQUIRE(N * H * W < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv3x3: more than 2^31 pixels");
   if (N == 0) return 0;
   MVP_REQUIRE(x1 && w_packed && bias && (out_planar || out_nhwc) && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3: null pointer");
@@ -585,7 +594,7 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   a.C1 = (int)C1; a.C2 = (int)C2; a.N = (int)N; a.H = (int)H; a.W = (int)W;
   a.wp = (const unsigned char *)w_packed; a.bias = bias; a.res = (const __nv_bfloat16 *)residual;
   a.out_p = (__nv_bfloat16 *)out_planar; a.out_f = out_nhwc; a.plane_out = Np * Cout * H * W; a.relu = relu;
-  a.Cout = (int)Cout; a.Nt = Cout <= 256 ? (int)Cout : 256; a.NB = a.Cout / a.Nt;
+  a.Cout = (int)Cout; a.Nt = (int)mvp_tc_conv3x3_nt(Cout); a.NB = a.Cout / a.Nt;
   a.ipt = pair ? 2 : 1;
   a.TX = (int)((W + 7) / 8);
   a.TY = pair ? 1 : (int)((H + 15) / 16);

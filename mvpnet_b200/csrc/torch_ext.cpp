@@ -624,6 +624,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
   fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
   fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv on split-planar activations, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
+  fz.def("tc_conv3x3_nt", &mvp_tc_conv3x3_nt, "output-channel block width of the packed 3x3 weights");
   fz.def("tc_conv_general", &tc_conv_general, "tap-staged conv / 2x2 transposed conv on split-planar activations (tcgen05)");
   fz.def("unfold_stem", &unfold_stem, "fp32 NCHW image -> row-unfolded split-planar (32 channels) for the 7x7 stem");
   fz.def("maxpool3x3s2_planar", &maxpool3x3s2_planar, "3x3/s2/p1 max-pool on split-planar activations");

@@ -55,7 +55,8 @@ def pack_conv3x3(weight, bias):
     """weight (Cout, Cin, 3, 3), bias (Cout) -> (packed, fp32 bias) for mvp_tc_conv3x3 (tap = ky*3 + kx)."""
     cout, cin = weight.shape[0], weight.shape[1]
     assert weight.shape[2:] == (3, 3)
-    return pack_taps(weight.reshape(cout, cin, 9), _nt(cout)), bias.float().contiguous()
+    nt = int(load_ext().fused_cuda.tc_conv3x3_nt(cout))              # the kernel's block width is part of the layout
+    return pack_taps(weight.reshape(cout, cin, 9), nt), bias.float().contiguous()
 
 
 def pack_conv_taps(weight, bias):
@@ -104,9 +105,19 @@ class Planar:
         return load_ext().fused_cuda.merge_planar(self.data, self.n, self.h, self.w, self.c)
 
 
+def _stage(name):
+    from . import engine          # bench.py's per-stage CUDA-event timers (no-op otherwise)
+    return engine._stage(name)
+
+
 def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=False):
     """x1 [, x2]: Planar inputs (concatenated along channels); residual: Planar or None.
     Returns a Planar, or an fp32 (N, H, W, Cout) tensor when nhwc_out."""
+    with _stage('net_2d/conv3x3'):
+        return _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out)
+
+
+def _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out):
     out = load_ext().fused_cuda.tc_conv3x3(x1.data, x1.c, None if x2 is None else x2.data, 0 if x2 is None else x2.c,
                                            x1.n, x1.h, x1.w, packed, bias, None if residual is None else residual.data, relu, nhwc_out)
     return out if nhwc_out else Planar(out, x1.n, x1.h, x1.w, bias.numel())
@@ -115,18 +126,21 @@ def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=False)
 def conv_general(x, packed, bias, dy, dx, stride=1, relu=True):
     """taps (dy, dx) convolution with stride 1 or 2 on a Planar (mvp_tc_conv_general mode 0)."""
     ho, wo = (x.h - 1) // stride + 1, (x.w - 1) // stride + 1
-    out = load_ext().fused_cuda.tc_conv_general(x.data, x.c, x.n, x.h, x.w, 0, stride, dy, dx, ho, wo, packed, bias, relu)
+    with _stage('net_2d/conv_general'):
+        out = load_ext().fused_cuda.tc_conv_general(x.data, x.c, x.n, x.h, x.w, 0, stride, dy, dx, ho, wo, packed, bias, relu)
     return Planar(out, x.n, ho, wo, bias.numel())
 
 
 def deconv2x2(x, packed, bias, relu=True):
     """2x2 / stride-2 transposed convolution on a Planar (mvp_tc_conv_general mode 1)."""
-    out = load_ext().fused_cuda.tc_conv_general(x.data, x.c, x.n, x.h, x.w, 1, 1, [0], [0], 2 * x.h, 2 * x.w, packed, bias, relu)
+    with _stage('net_2d/conv_general'):
+        out = load_ext().fused_cuda.tc_conv_general(x.data, x.c, x.n, x.h, x.w, 1, 1, [0], [0], 2 * x.h, 2 * x.w, packed, bias, relu)
     return Planar(out, x.n, 2 * x.h, 2 * x.w, bias.numel())
 
 
 def maxpool3x3s2(x):
-    out = load_ext().fused_cuda.maxpool3x3s2_planar(x.data, x.n, x.h, x.w, x.c)
+    with _stage('net_2d/pool_unfold'):
+        out = load_ext().fused_cuda.maxpool3x3s2_planar(x.data, x.n, x.h, x.w, x.c)
     return Planar(out, x.n, (x.h - 1) // 2 + 1, (x.w - 1) // 2 + 1, x.c)
 
 
@@ -166,7 +180,8 @@ class FastUNetResNet34:
         if pad_h or pad_w:
             x = F.pad(x, [0, pad_w, 0, pad_h])
         hp, wp = h + pad_h, w + pad_w
-        x = Planar(load_ext().fused_cuda.unfold_stem(x.contiguous()), n, hp, wp, 32)
+        with _stage('net_2d/pool_unfold'):
+            x = Planar(load_ext().fused_cuda.unfold_stem(x.contiguous()), n, hp, wp, 32)
         x = conv_general(x, *self.stem, stride=1, relu=True)
         skips = [x]
         x = maxpool3x3s2(x)

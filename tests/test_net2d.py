@@ -15,8 +15,12 @@ def unpack_taps(packed, cin, g, t, nt):
     return x[0], x[1]
 
 
+def conv3x3_nt(cout):
+    return min(cout, 256)            # mvp_tc_conv3x3_nt
+
+
 def unpack_conv3x3(packed, cin, cout):
-    hi, lo = unpack_taps(packed, cin, cout, 9, cout if cout <= 256 else 256)
+    hi, lo = unpack_taps(packed, cin, cout, 9, conv3x3_nt(cout))
     return hi.reshape(cout, cin, 3, 3), lo.reshape(cout, cin, 3, 3)
 
 
@@ -55,7 +59,13 @@ def emulated_general(x, mode, stride, dy, dx, ho, wo, packed, bias, relu):
     return (y.clamp_min(0) if relu else y).float().contiguous()
 
 
-def test_pack_round_trip():
+def test_pack_round_trip(monkeypatch):
+    class _F:
+        tc_conv3x3_nt = staticmethod(conv3x3_nt)
+
+    class _E:
+        fused_cuda = _F
+    monkeypatch.setattr(net2d, 'load_ext', lambda: _E)
     torch.manual_seed(0)
     for cin, cout in [(64, 64), (128, 64), (256, 512), (512, 256)]:
         w = torch.randn(cout, cin, 3, 3)
@@ -76,6 +86,10 @@ def test_plan_matches_module_features(monkeypatch):
 
     class _Fused:
         """CPU stand-ins with the extension's signatures: a "planar" tensor is simply the flat fp32 NHWC data."""
+        @staticmethod
+        def tc_conv3x3_nt(cout):
+            return conv3x3_nt(cout)
+
         @staticmethod
         def split_planar(x):
             return x.reshape(-1).clone()
