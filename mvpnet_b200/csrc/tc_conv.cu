@@ -325,41 +325,39 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
       uint32_t first = 0u;
       for (int c = 0; c < a.nchunks; ++c) {
         mbar_wait(bar_afull + 8 * ss, a_ph);
-        uint32_t a_tap_lo = a_lo0 + ss * set16;               // tap (-1, -1): the patch origin
-        uint32_t b_lo = 0;
-        int in_stage = 0;                                     // taps of the current weight stage already used
-#pragma unroll 1
-        for (int dy = 0; dy < 3; ++dy) {
+        const uint32_t a_org_lo = a_lo0 + ss * set16;          // tap (-1, -1): the patch origin
+        // One weight stage holds tps taps (a filter row, or the whole 3x3).  Within a stage the loops run tile-outer,
+        // tap-inner: consecutive MMAs accumulate into the SAME TMEM tile (3 x tps of them) before the accumulator
+        // changes — switching accumulators after every tap cost a pipeline bubble per switch on the narrow layers.
+        for (int st = 0; st < 9; st += a.tps) {
+          mbar_wait(bar_bfull + 8 * s, b_ph);
+          const uint32_t b_lo = b_lo0 + s * stage16;
+          if (elect_one()) {
+            if (!(a.dbg & 16)) {
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            if (in_stage == 0) {
-              mbar_wait(bar_bfull + 8 * s, b_ph);
-              b_lo = b_lo0 + s * stage16;
-            }
-            const uint64_t bh = desc64(b_lo, b_hi32), bl = desc64(b_lo + lo_of_hi, b_hi32);
-            const bool last = in_stage + 1 == a.tps;
-            if (elect_one()) {
-              if (!(a.dbg & 16)) {
-#pragma unroll
-                for (int t = 0; t < MAX_TM; ++t) {
-                  if (t < nt) {
-                    const uint32_t lo = a_tap_lo + (uint32_t)dx + (uint32_t)(t * (SLOT_BYTES >> 4));
+              for (int t = 0; t < MAX_TM; ++t) {
+                if (t < nt) {
+                  const uint32_t d = d0 + (uint32_t)(t * a.Nt);
+                  const uint32_t a_t = a_org_lo + (uint32_t)(t * (SLOT_BYTES >> 4));
+                  uint32_t acc = first, bt = b_lo;
+                  for (int j = 0; j < a.tps; ++j, bt += tap16) {
+                    const int tap = st + j, dy = tap / 3, dx = tap - dy * 3;
+                    const uint32_t lo = a_t + (uint32_t)dy * row16 + (uint32_t)dx;
                     const uint64_t ah = desc64(lo, a_hi32), al = desc64(lo + (SLOT_HALF >> 4), a_hi32);
-                    const uint32_t d = d0 + (uint32_t)(t * a.Nt);
-                    umma_bf16(d, ah, bh, idesc, first);
+                    const uint64_t bh = desc64(bt, b_hi32), bl = desc64(bt + lo_of_hi, b_hi32);
+                    umma_bf16(d, ah, bh, idesc, acc);
                     umma_bf16(d, ah, bl, idesc, 1u);
                     umma_bf16(d, al, bh, idesc, 1u);
+                    acc = 1u;
                   }
                 }
               }
-              if (last) { if (a.dbg & 64) mbar_arrive(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s); }
             }
-            __syncwarp();
-            first = 1u;
-            b_lo += tap16;
-            if (last) { in_stage = 0; if (++s == S) { s = 0; b_ph ^= 1u; } } else { ++in_stage; }
+            if (a.dbg & 64) mbar_arrive(bar_bempty + 8 * s); else umma_commit(bar_bempty + 8 * s);
           }
-          a_tap_lo += row16;
+          __syncwarp();
+          first = 1u;
+          if (++s == S) { s = 0; b_ph ^= 1u; }
         }
         if (elect_one()) umma_commit(bar_aempty + 8 * ss);
         __syncwarp();
@@ -602,17 +600,27 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   // accumulators: two sets (epilogue overlaps the next group's MMAs) where 2 x TM x Nt columns fit TMEM
   a.TM = a.Nt <= 64 ? 4 : 2;
   a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
-  // spread over the SMs before stacking tiles on one CTA
-  while (a.TM > 1 && (a.ntiles + a.TM - 1) / a.TM * a.NB < sm_count()) a.TM >>= 1;
+  // tiles per work item: the largest TM whose makespan (rounds of work items over the SMs x item length) is minimal —
+  // few-tile layers (the 8 x 10 level: 160 tiles) balance better with shorter items, at the price of weight traffic
+  {
+    long long best = -1;
+    int best_tm = 1;
+    for (int tm = a.TM; tm >= 1; tm >>= 1) {
+      const long long works = (a.ntiles + tm - 1) / tm * a.NB, span = (works + sm_count() - 1) / sm_count() * tm;
+      if (best < 0 || span < best) { best = span; best_tm = tm; }
+    }
+    a.TM = best_tm;
+  }
   a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
   a.nchunks = (int)((C1 + C2) / 16);
   a.tmem_cols = 32;
   while (a.tmem_cols < a.nacc * a.TM * a.Nt) a.tmem_cols <<= 1;
   a.asets = tcc::MAX_ASETS;
   a.stages = tcc::MAX_STAGES;
-  // taps per weight stage: a whole chunk (9 taps) for narrow layers, one filter row otherwise — every stage costs
-  // the issuer one barrier round trip, which a single N <= 64 tap (12 short MMAs) does not cover
-  a.tps = a.Nt <= 64 ? 9 : 3;
+  // taps per weight stage: the whole 3x3 (9 taps) where two such stages fit shared memory, one filter row otherwise —
+  // all MMAs of a stage on one tile accumulate back to back into the same TMEM tile (see the issuer), and every
+  // stage costs the issuer one barrier round trip
+  a.tps = a.Nt <= 128 ? 9 : 3;
   {
     const char *e = getenv("MVPNET_B200_CONV_DBG");
     a.dbg = e ? atoi(e) : 0;
