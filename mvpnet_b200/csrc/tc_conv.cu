@@ -610,6 +610,7 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
       if (best < 0 || span < best) { best = span; best_tm = tm; }
     }
     a.TM = best_tm;
+    a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
   }
   a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
   a.nchunks = (int)((C1 + C2) / 16);
