@@ -30,6 +30,8 @@
 //     mbarrier hand-offs throughout.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mvp {
@@ -510,6 +512,8 @@ static unsigned int *sched_pair() {
   constexpr int DEVICES = 64, PAIRS = 64;
   static unsigned int *pool[DEVICES] = {};
   static unsigned int next[DEVICES] = {};
+  static std::mutex mu;                              // nn.DataParallel calls in from one thread per GPU
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= DEVICES) return nullptr;
