@@ -179,7 +179,7 @@ def stage_bound(name):
 # stem unfold 1, max-pool 1); ATen adds 11 small copies / gathers
 KERNELS_PER_STEP = 83
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (MB) from the committed ncu capture (profiles/r1_ncu_*.md)
-NCU_TRAFFIC_MB = {}
+NCU_TRAFFIC_MB = {'net_2d/conv3x3': 285.7}     # profiles/r1_ncu_full_final.md: 9429 MB over the 33 launches of one step
 
 
 def tensor_peak():

@@ -1,6 +1,6 @@
 """Markdown table from an ncu report (raw page): one row per captured launch with the metrics the roofline uses.
 
-  python tools/ncu_summary.py REPORT.ncu-rep > profiles/<name>.md
+  python tools/ncu_summary.py REPORT.ncu-rep|RAW.csv > profiles/<name>.md
 """
 import csv
 import io
@@ -21,7 +21,10 @@ def to_mb(v, unit):
 
 
 def main():
-    out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    if sys.argv[1].endswith('.csv'):                 # already exported with `ncu -i X.ncu-rep --page raw --csv`
+        out = open(sys.argv[1]).read()
+    else:
+        out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
