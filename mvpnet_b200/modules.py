@@ -339,3 +339,41 @@ class MVPNet3D(nn.Module):
         """Inference through the fused sm_100a kernels (mvpnet_b200/engine.py); same result contract."""
         from . import engine
         return engine.mvpnet3d_forward(self, data_batch, overlap=overlap)
+
+
+class MVPNet2D(nn.Module):
+    """2D network only: per-pixel logits gathered at the k nearest pixels of every point and averaged
+    (mvpnet/models/mvpnet_2d.py:7-34).  data_batch keys: images (b,nv,3,h,w), knn_indices (b,np,k)."""
+
+    def __init__(self, net_2d):
+        super().__init__()
+        self.net_2d = net_2d
+
+    def forward(self, data_batch):
+        images = data_batch['images']
+        b, nv, _, h, w = images.size()
+        seg_logit_2d = self.net_2d({'image': images.reshape([-1] + list(images.shape[2:]))})['seg_logit']
+        knn_indices = data_batch['knn_indices']
+        seg_logit = seg_logit_2d.reshape(b, nv, -1, h, w).transpose(1, 2).contiguous().reshape(b, -1, nv * h * w)
+        return {'seg_logit': group_points(seg_logit, knn_indices).mean(-1)}
+
+    def fast_forward(self, data_batch):
+        """Inference on the tensor-core 2D network (net2d.py).  The 1x1 logit head is linear, so it is applied AFTER
+        the gather + mean over the k pixels: 64-channel rows of the NHWC feature map are gathered (one 256-byte row
+        per pixel) instead of materialising per-pixel logits for every view."""
+        from . import engine
+        images, knn = data_batch['images'], data_batch['knn_indices']
+        engine._require_eval_fp32(self, images)
+        plan = engine._tc_net2d(self.net_2d)
+        if plan is None:
+            return self.forward(data_batch)
+        b, nv, _, h, w = images.size()
+        feat = plan.features_nhwc(images.reshape(b * nv, *images.shape[2:]))          # (b*nv, h, w, c) view of padded rows
+        c = feat.size(3)
+        pix = knn.reshape(b, -1)                                                      # flat pixel ids v*h*w + y*w + x
+        v, rem = pix // (h * w), pix % (h * w)
+        rows = feat[(torch.arange(b, device=pix.device).unsqueeze(1) * nv + v), rem // w, rem % w]   # (b, np*k, c)
+        mean = rows.reshape(b, knn.size(1), knn.size(2), c).mean(dim=2)                # (b, np, c)
+        head = self.net_2d.logit
+        logit = torch.matmul(mean, head.weight.reshape(head.out_channels, c).t()) + head.bias
+        return {'seg_logit': logit.transpose(1, 2).contiguous()}
