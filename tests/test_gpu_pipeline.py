@@ -32,5 +32,5 @@ def test_pipelined_forward_returns_each_submissions_result():
             want = torch.full((4,), float(i))
             for _ in range(20):
                 want = torch.sin(want) + 0.5 * i
-            assert torch.allclose(o[:4], want, atol=1e-5) and torch.allclose(o[-4:], want, atol=1e-5), i
+            assert torch.allclose(o[:4], want, atol=1e-4) and torch.allclose(o[-4:], want, atol=1e-4), i
     torch.cuda.synchronize()
