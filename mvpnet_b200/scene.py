@@ -6,6 +6,9 @@
     and prediction counts over the chunks, mean, arg-max, points without prediction labelled `num_classes`.  The adds
     happen chunk by chunk in call order (indices inside a chunk are unique), so the fp32 sums are the reference's.
 
+  * `select_frames` — greedy choice of the RGB-D frames that cover the most still-uncovered base points
+    (mvpnet/data/scannet_2d3d.py:20-30), ties resolved like numpy's argmax (lowest frame index).
+
 Pure torch (index arithmetic and bandwidth-bound adds): runs on CPU tensors too, which is how the CPU tests pin it
 against the reference's own numpy code (tests/golden/make_golden_scene.py).
 """
@@ -68,3 +71,17 @@ class VoteAccumulator:
         label = mean.argmax(dim=1)
         label[self.count == 0] = self.num_classes
         return mean, label
+
+
+def select_frames(rgbd_overlap, num_rgbd_frames):
+    """rgbd_overlap (num_basepoints, num_frames) bool tensor: point p is seen by frame f.  Returns the list of
+    `num_rgbd_frames` frame indices chosen greedily by remaining coverage (scannet_2d3d.py:20-30)."""
+    overlap = rgbd_overlap.clone()             # the reference copies too: the input is not modified
+    selected = []
+    for _ in range(num_rgbd_frames):
+        counts = overlap.sum(dim=0)
+        # first index of the maximum, as numpy.argmax (torch.argmax does not promise which of several maxima)
+        frame_idx = int(torch.nonzero(counts == counts.max(), as_tuple=False)[0])
+        selected.append(frame_idx)
+        overlap[overlap[:, frame_idx].clone()] = False  # every point covered by this frame stops counting (mask copied: it aliases the target)
+    return selected

@@ -34,6 +34,28 @@ def scene_points(seed=11, n=60000):
     return pts[rng.permutation(len(pts))]
 
 
+def reference_select_frames():
+    """mvpnet/data/scannet_2d3d.py:20-30, taken from the source file by AST (the module itself imports open3d)."""
+    import ast
+    src = open('/root/reference/mvpnet/data/scannet_2d3d.py').read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'select_frames'][0]
+    ns = {'np': np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'scannet_2d3d.py', 'exec'), ns)
+    return ns['select_frames']
+
+
+def overlap_matrix(seed=3, num_points=5000, num_frames=40):
+    """Synthetic visibility: every frame sees the points inside a random cone-ish window; several exact ties."""
+    rng = np.random.RandomState(seed)
+    centre = rng.rand(num_frames, 1) * num_points
+    width = rng.randint(200, 1500, size=(num_frames, 1))
+    idx = np.arange(num_points)[None, :]
+    m = (np.abs(idx - centre) < width) & (rng.rand(num_frames, num_points) < 0.8)
+    m[7] = m[3]                                   # duplicated frames: equal coverage, the lower index must win
+    m[21] = m[20]
+    return np.ascontiguousarray(m.T)
+
+
 def main():
     pts = scene_points()
     idx, bbox = chunk_util.scene2chunks_legacy(pts, chunk_size=(1.5, 1.5), stride=0.5, thresh=1000, margin=(0.2, 0.2), return_bbox=True)
@@ -57,7 +79,9 @@ def main():
                         chunk_index_checksums=np.array([int(i.astype(np.int64).sum()) for i in idx]),
                         first_chunk=idx[0], bboxes=np.stack(bbox), count=count, label=label.astype(np.int64),
                         mean_sample=mean[::97], mean_checksum=np.float64(mean.astype(np.float64).sum()))
-    print('chunks', len(idx), 'points without prediction', int((count == 0).sum()))
+    sel = {str(k): np.array(reference_select_frames()(overlap_matrix(), k)) for k in (1, 3, 5, 12)}
+    np.savez_compressed(os.path.join(HERE, 'select_frames.npz'), **sel)
+    print('chunks', len(idx), 'points without prediction', int((count == 0).sum()), 'frames', sel['5'])
 
 
 if __name__ == '__main__':

@@ -18,10 +18,36 @@ def _scene_points():
     # the generator's point sampler without importing the reference (absent on the GPU box)
     src = open(os.path.join(HERE, 'golden', 'make_golden_scene.py')).read()
     ns = {}
-    start, end = src.index('def scene_points'), src.index('def main')
+    start, end = src.index('def scene_points'), src.index('def reference_select_frames')
     from mvpnet_b200 import synthetic
     exec(src[start:end], {'np': np, 'synthetic': synthetic}, ns)
     return ns['scene_points']()
+
+
+def _overlap_matrix():
+    src = open(os.path.join(HERE, 'golden', 'make_golden_scene.py')).read()
+    ns = {}
+    start, end = src.index('def overlap_matrix'), src.index('def main')
+    exec(src[start:end], {'np': np}, ns)
+    return ns['overlap_matrix']()
+
+
+def _check_frames(device):
+    g = np.load(os.path.join(HERE, 'golden', 'select_frames.npz'))
+    m = torch.from_numpy(_overlap_matrix()).to(device)
+    keep = m.clone()
+    for k in (1, 3, 5, 12):
+        assert scene.select_frames(m, k) == g[str(k)].tolist()
+    assert torch.equal(m, keep)                   # input untouched
+
+
+def test_select_frames_cpu():
+    _check_frames('cpu')
+
+
+@pytest.mark.gpu
+def test_select_frames_gpu():
+    _check_frames('cuda')
 
 
 def _check(device):
