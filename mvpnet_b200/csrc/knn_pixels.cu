@@ -235,10 +235,13 @@ kp_scan_kernel(const KpGrid *__restrict__ grids, int *__restrict__ cells) {
   for (int i = lo; i < hi; ++i) { const int t = c[i]; c[i] = run; run += t; }
 }
 
+// one sorted pixel: 32 bytes, read by the query kernel as two 16-byte loads
+struct __align__(16) KpRec { double x, y, z; long long id; };
+
 // scatter: cells[] enters as the start offsets and leaves as the END offsets of every cell
 __global__ void __launch_bounds__(256)
 kp_scatter_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ mask, int P, const KpGrid *__restrict__ grids,
-                  int *__restrict__ cells, double *__restrict__ sorted_xyz, int *__restrict__ sorted_id) {
+                  int *__restrict__ cells, KpRec *__restrict__ sorted) {
   const int b = blockIdx.y;
   const int p = blockIdx.x * 256 + threadIdx.x;
   if (p >= P || !mask[(size_t)b * P + p]) return;
@@ -248,15 +251,15 @@ kp_scatter_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ ma
   const int c = (cell_coord(z, g.oz, g.inv_s, g.gz) * g.gy + cell_coord(y, g.oy, g.inv_s, g.gy)) * g.gx +
                 cell_coord(x, g.ox, g.inv_s, g.gx);
   const int pos = atomicAdd(cells + (size_t)b * (KP_CELL_CAP + 1) + c, 1);
-  double *o = sorted_xyz + ((size_t)b * P + pos) * 3;
-  o[0] = x; o[1] = y; o[2] = z;
-  sorted_id[(size_t)b * P + pos] = p;
+  KpRec r;
+  r.x = x; r.y = y; r.z = z; r.id = p;
+  sorted[(size_t)b * P + pos] = r;
 }
 
 template <int KMAX>
 __global__ void __launch_bounds__(256)
 kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ grids, const int *__restrict__ cells,
-                const double *__restrict__ sorted_xyz, const int *__restrict__ sorted_id, int nq, int P, int k,
+                const KpRec *__restrict__ sorted, int nq, int P, int k,
                 int blocks_per_cloud, int64_t *__restrict__ index, double *__restrict__ dist2) {
   const int b = blockIdx.x / blocks_per_cloud;
   const int q = (blockIdx.x % blocks_per_cloud) * 8 + (threadIdx.x >> 5);
@@ -264,8 +267,7 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
   if (q >= nq) return;  // warp-uniform
   const KpGrid g = grids[b];
   const int *ends = cells + (size_t)b * (KP_CELL_CAP + 1);
-  const double *sx = sorted_xyz + (size_t)b * P * 3;
-  const int *sid = sorted_id + (size_t)b * P;
+  const KpRec *srec = sorted + (size_t)b * P;
   const double *qp = query + ((size_t)b * nq + q) * 3;
   const double qx = qp[0], qy = qp[1], qz = qp[2];
   const int cx = cell_coord(qx, g.ox, g.inv_s, g.gx), cy = cell_coord(qy, g.oy, g.inv_s, g.gy), cz = cell_coord(qz, g.oz, g.inv_s, g.gz);
@@ -276,9 +278,19 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) { bd[j] = Inf<double>::v(); bi[j] = 0x7fffffff; }
 
-  auto scan = [&](int beg, int end) {  // a contiguous run of the sorted pixel array, lanes in parallel
-    for (int p = beg + lane; p < end; p += 32)
-      topk_insert<KMAX>(sqdist3_nofma(sx[3 * (size_t)p], sx[3 * (size_t)p + 1], sx[3 * (size_t)p + 2], qx, qy, qz), sid[p], bd, bi);
+  // a contiguous run of the sorted pixel array, lanes in parallel.  The kernel is bound by the latency of these loads
+  // (profile: 55 % of the stall samples on them, L2 at 11 %): every trip fetches the records of TWO sub-iterations
+  // (two 16-byte loads each) before it evaluates either, which doubles the loads in flight per warp.
+  auto scan = [&](int beg, int end) {
+    for (int p0 = beg; p0 < end; p0 += 64) {
+      const int pa = p0 + lane, pb = p0 + 32 + lane;
+      const bool oka = pa < end, okb = pb < end;
+      double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+      if (oka) { const double2 *r = reinterpret_cast<const double2 *>(srec + pa); a0 = __ldg(r); a1 = __ldg(r + 1); }
+      if (okb) { const double2 *r = reinterpret_cast<const double2 *>(srec + pb); b0 = __ldg(r); b1 = __ldg(r + 1); }
+      if (oka) topk_insert<KMAX>(sqdist3_nofma(a0.x, a0.y, a1.x, qx, qy, qz), (int)__double_as_longlong(a1.y), bd, bi);
+      if (okb) topk_insert<KMAX>(sqdist3_nofma(b0.x, b0.y, b1.x, qx, qy, qz), (int)__double_as_longlong(b1.y), bd, bi);
+    }
   };
 
   double kth = Inf<double>::v();   // k-th best squared distance over the whole warp so far
@@ -371,7 +383,7 @@ extern "C" int64_t mvp_knn_pixels_workspace_bytes(int64_t B, int64_t nq, int64_t
   (void)nq; (void)k;
   if (B <= 0 || P <= 0) return 0;
   return (int64_t)(kp_align(sizeof(KpGrid) * B) + kp_align(sizeof(int) * (size_t)B * (KP_CELL_CAP + 1)) +
-                   kp_align(sizeof(double) * (size_t)B * P * 3) + kp_align(sizeof(int) * (size_t)B * P));
+                   kp_align(sizeof(KpRec) * (size_t)B * P));
 }
 
 extern "C" int mvp_knn_pixels(const double *query, const double *pix_xyz, const uint8_t *mask, int64_t B, int64_t nq,
@@ -399,8 +411,7 @@ extern "C" int mvp_knn_pixels(const double *query, const double *pix_xyz, const 
   unsigned char *w = (unsigned char *)workspace;
   KpGrid *grids = (KpGrid *)w;                     w += kp_align(sizeof(KpGrid) * B);
   int *cells = (int *)w;                           w += kp_align(sizeof(int) * (size_t)B * (KP_CELL_CAP + 1));
-  double *sorted_xyz = (double *)w;                w += kp_align(sizeof(double) * (size_t)B * P * 3);
-  int *sorted_id = (int *)w;
+  KpRec *sorted = (KpRec *)w;
   cudaError_t e = cudaMemsetAsync(cells, 0, sizeof(int) * (size_t)B * (KP_CELL_CAP + 1), stream);
   if (e != cudaSuccess) { set_error("knn_pixels: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
   static const double cell_scale = [] { const char *e = getenv("MVPNET_B200_KP_CELL_SCALE"); const double v = e ? atof(e) : 0.0; return v > 0.0 ? v : KP_CELL_SCALE; }();
@@ -408,13 +419,13 @@ extern "C" int mvp_knn_pixels(const double *query, const double *pix_xyz, const 
   dim3 pgrid((unsigned)((P + 255) / 256), (unsigned)B);
   kp_count_kernel<<<pgrid, 256, 0, stream>>>(pix_xyz, mask, (int)P, grids, cells);
   kp_scan_kernel<<<(unsigned)B, 1024, 0, stream>>>(grids, cells);
-  kp_scatter_kernel<<<pgrid, 256, 0, stream>>>(pix_xyz, mask, (int)P, grids, cells, sorted_xyz, sorted_id);
+  kp_scatter_kernel<<<pgrid, 256, 0, stream>>>(pix_xyz, mask, (int)P, grids, cells, sorted);
   const int bpc = (int)((nq + 7) / 8);
   const int64_t grid = B * bpc;
   MVP_REQUIRE(grid < (1LL << 31), MVP_ERR_UNSUPPORTED, "knn_pixels: too many queries");
   if (k <= 3)
-    kp_query_kernel<3><<<(unsigned)grid, 256, 0, stream>>>(query, grids, cells, sorted_xyz, sorted_id, (int)nq, (int)P, (int)k, bpc, index, dist2);
+    kp_query_kernel<3><<<(unsigned)grid, 256, 0, stream>>>(query, grids, cells, sorted, (int)nq, (int)P, (int)k, bpc, index, dist2);
   else
-    kp_query_kernel<8><<<(unsigned)grid, 256, 0, stream>>>(query, grids, cells, sorted_xyz, sorted_id, (int)nq, (int)P, (int)k, bpc, index, dist2);
+    kp_query_kernel<8><<<(unsigned)grid, 256, 0, stream>>>(query, grids, cells, sorted, (int)nq, (int)P, (int)k, bpc, index, dist2);
   return launch_status("knn_pixels");
 }
