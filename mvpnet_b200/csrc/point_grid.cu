@@ -366,17 +366,10 @@ pg_knn3_kernel(const T *__restrict__ query, const PgGrid<T> *__restrict__ grids,
 
   T bd[3] = {Inf<T>::v(), Inf<T>::v(), Inf<T>::v()};
   int bi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
-  // a contiguous run of the sorted key array, lanes in parallel; two sub-iterations' records are fetched before either
-  // is evaluated (the walk is bound by the latency of these loads, see knn_pixels.cu)
-  auto scan = [&](int beg, int end) {
-    for (int p0 = beg; p0 < end; p0 += 64) {
-      const int pa = p0 + lane, pb = p0 + 32 + lane;
-      const bool oka = pa < end, okb = pb < end;
-      PgRec<T> ka, kb;
-      if (oka) ka = pg_load<T>(sp + pa);
-      if (okb) kb = pg_load<T>(sp + pb);
-      if (oka) pg_top3_insert(sqdist3(ka.x, ka.y, ka.z, qx, qy, qz), (int)ka.i, bd, bi);
-      if (okb) pg_top3_insert(sqdist3(kb.x, kb.y, kb.z, qx, qy, qz), (int)kb.i, bd, bi);
+  auto scan = [&](int beg, int end) {  // a contiguous run of the sorted key array, lanes in parallel
+    for (int p = beg + lane; p < end; p += 32) {
+      const PgRec<T> k = pg_load<T>(sp + p);
+      pg_top3_insert(sqdist3(k.x, k.y, k.z, qx, qy, qz), (int)k.i, bd, bi);
     }
   };
 
