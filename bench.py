@@ -377,7 +377,7 @@ def main():
         return d
 
     from mvpnet_b200.distributed import all_gather_chunks
-    gathered = torch.empty(world * cpg, NUM_CLASSES, NUM_POINTS, device=device) if world > 1 else None
+    gathered = [torch.empty(world * cpg, NUM_CLASSES, NUM_POINTS, device=device) for _ in range(4)] if world > 1 else None
     host_out = torch.empty(cpg, NUM_CLASSES, NUM_POINTS).pin_memory()
 
     graphed = {'fn': None, 'note': 'eager launches'}
@@ -386,12 +386,32 @@ def main():
         return {'images': dev['images'], 'points': dev['points_cm'], 'depth': dev['depth'], 'pose': dev['pose'],
                 'cam_inv': dev['cam_inv'], 'chunk_box': dev['chunk_box'], 'k': KNN}
 
-    def step_device(dev):
+    def step_device(dev, lane=0):
         with torch.no_grad():
-            logit = graphed['fn'](batch_of(dev)) if graphed['fn'] is not None else hot_path(model, dev)
+            fn = lane_graphs[lane] if lane_graphs else graphed['fn']
+            logit = fn(batch_of(dev)) if fn is not None else hot_path(model, dev)
             if world > 1:
-                all_gather_chunks(logit, world * cpg, out=gathered)
+                all_gather_chunks(logit, world * cpg, out=gathered[lane])
         return logit
+
+    step_no = {'i': 0}
+
+    def step_device_laned(dev):
+        """One step on the next lane's stream (device-resident inputs)."""
+        lane = step_no['i'] % lanes
+        step_no['i'] += 1
+        if lanes == 1:
+            return step_device(dev)
+        with torch.cuda.stream(lane_streams[lane]):
+            return step_device(dev, lane)
+
+    def lanes_begin():
+        for st in lane_streams[:lanes] if lanes > 1 else []:
+            st.wait_stream(torch.cuda.current_stream())
+
+    def lanes_drain():
+        for st in lane_streams[:lanes] if lanes > 1 else []:
+            torch.cuda.current_stream().wait_stream(st)
 
     def prepare(d):            # device-side view of a freshly uploaded host batch (what to_device does)
         dd = dict(d)
@@ -402,7 +422,7 @@ def main():
     # inputs and one D2H of the logits, on copy streams, double-buffered so that they overlap the neighbouring steps
     pipe = {}
     last = {}
-    e2e_mode = {'name': 'pipelined (engine.PipelinedForward: H2D / compute / D2H on three streams, two buffer sets)'}
+    e2e_mode = {'name': ''}
 
     def step_e2e():
         last['out'], last['ev'] = pipe['p'].submit(host)
@@ -417,10 +437,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n, drain=None):
+    def timed(fn, n, drain=None, begin=None):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        if begin is not None:       # other streams start after the start event
+            begin()
         for _ in range(n):
             fn()
         if drain is not None:       # work left on other streams (the last download) belongs to the timed region
@@ -434,22 +456,35 @@ def main():
         return float(ms.item())
 
     dev = to_device(host)
+    # Lanes: consecutive steps alternate between `lanes` independent CUDA graphs on their own streams, so that the
+    # under-occupied tail of one step (small set-abstraction / propagation levels, 30-150 CTAs) runs beside the
+    # convolutions of the next one; the persistent convolution kernels share SMs through their dynamic work distribution.
+    lanes = min(4, max(1, int(os.environ.get('MVPNET_B200_BENCH_LANES', '2'))))
+    lane_graphs, lane_streams = [], []
     if not args.no_cuda_graph and not args.no_extras:
         try:
             graphed['fn'] = engine.GraphedForward(model, batch_of(dev))
             graphed['note'] = 'one CUDA graph replay per step (2D network + both streams captured)'
+            lane_graphs = [graphed['fn']] + [engine.GraphedForward(model, batch_of(dev)) for _ in range(lanes - 1)]
+            lane_streams = [torch.cuda.Stream(device) for _ in range(lanes)]
+            if lanes > 1:
+                graphed['note'] += '; consecutive steps alternate between %d graphs on %d streams' % (lanes, lanes)
         except Exception as ex:      # capture is an optimisation; never lose the measurement over it
             graphed['fn'] = None
+            lane_graphs, lane_streams = [], []
             graphed['note'] = 'eager launches (graph capture failed: %s)' % str(ex)[:120]
             torch.cuda.synchronize()
+    lanes = len(lane_graphs) if len(lane_graphs) > 1 else 1
     config['launch_mode'] = graphed['note']
+    lanes_begin()
     for _ in range(warmup):
-        step_device(dev)
+        step_device_laned(dev)
+    lanes_drain()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     torch.cuda.nvtx.range_push('timed')          # ncu --nvtx --nvtx-include "timed/" captures exactly the timed steps
-    ms_total = timed(lambda: step_device(dev), args.steps)
+    ms_total = timed(lambda: step_device_laned(dev), args.steps, drain=lanes_drain, begin=lanes_begin)
     torch.cuda.nvtx.range_pop()
     clocks = sampler.summary() if rank == 0 else None
     if args.no_extras:
@@ -460,7 +495,10 @@ def main():
             dist.destroy_process_group()
         return
     try:
-        pipe['p'] = engine.PipelinedForward(step_device, host, device, prepare=prepare, depth=2)
+        e2e_mode['name'] = 'pipelined (engine.PipelinedForward: H2D / compute / D2H on separate streams, two buffer sets%s)' % (
+            ', one compute lane per buffer set' if lanes > 1 else '')
+        fwd = [(lambda d, l=l: step_device(d, l)) for l in range(lanes)] if lanes > 1 else step_device
+        pipe['p'] = engine.PipelinedForward(fwd, host, device, prepare=prepare, depth=2)
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps, drain=lambda: torch.cuda.current_stream().wait_event(last['ev']))

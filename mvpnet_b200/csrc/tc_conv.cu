@@ -507,9 +507,11 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // device-resident {next, retired} counter pairs for the dynamic work distribution, handed out round-robin per launch;
-// a pair re-arms itself when its launch retires, so only > 64 launches in flight at once could ever share one
+// a pair re-arms itself when its launch retires, so only launches 4096 apart in issue order could ever share one
+// (a captured CUDA graph keeps the pairs its launches drew at capture time: two graphs replayed concurrently hold
+// disjoint ranges as long as fewer than 4096 launches were issued between their captures)
 static unsigned int *sched_pair() {
-  constexpr int DEVICES = 64, PAIRS = 64;
+  constexpr int DEVICES = 64, PAIRS = 4096;
   static unsigned int *pool[DEVICES] = {};
   static unsigned int next[DEVICES] = {};
   static std::mutex mu;                              // nn.DataParallel calls in from one thread per GPU

@@ -461,42 +461,55 @@ class GraphedForward:
 
 class PipelinedForward:
     """Throughput API from HOST buffers.  `submit(host_batch)` uploads the batch (pinned host tensors) on a copy stream,
-    runs `forward(prepare(device_batch))` on the current stream and downloads the result into a pinned host buffer on a
-    second copy stream; with `depth` >= 2 buffer sets the upload of batch i+1 and the download of batch i-1 overlap the
-    compute of batch i (PCIe is full duplex, the copy engines are idle otherwise).  Every submission still performs its
-    own H2D and D2H copies; nothing is cached between submissions.
+    runs `forward(prepare(device_batch))` and downloads the result into a pinned host buffer on a second copy stream;
+    with `depth` >= 2 buffer sets the upload of batch i+1 and the download of batch i-1 overlap the compute of batch i
+    (PCIe is full duplex, the copy engines are idle otherwise).  Every submission still performs its own H2D and D2H
+    copies; nothing is cached between submissions.
 
     forward: callable(device_batch) -> result tensor (may be a static CUDA-graph output: it is copied out before the
-    next submission can overwrite it).  Returns (pinned host tensor, event): the tensor holds the result once the event
-    has completed (or after torch.cuda.synchronize())."""
+    next submission of the same slot can overwrite it), or a LIST of `depth` callables, one per buffer set ("lanes"):
+    each lane then computes on its own stream, so that consecutive submissions overlap on the GPU as well — the
+    under-occupied tail of one forward (small set-abstraction / propagation levels) runs beside the convolutions of
+    the next.  Lane callables must not share mutable state (e.g. one GraphedForward per lane).
+    Returns (pinned host tensor, event): the tensor holds the result once the event has completed."""
 
     def __init__(self, forward, example_host_batch, device, prepare=None, depth=2):
+        self.lanes = isinstance(forward, (list, tuple))
+        if self.lanes:
+            depth = len(forward)
         self.forward, self.prepare, self.depth, self.i = forward, prepare, depth, 0
         self.h2d, self.d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.compute = [torch.cuda.Stream(device) for _ in range(depth)] if self.lanes else None
         self.slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in example_host_batch.items() if torch.is_tensor(v)}
                       for _ in range(depth)]
         ev = lambda: [torch.cuda.Event() for _ in range(depth)]
         self.in_ready, self.in_free, self.out_ready, self.out_free = ev(), ev(), ev(), ev()
-        self.out_dev = self.out_host = None
+        self.out_dev = [None] * depth
+        self.out_host = [None] * depth
 
     def submit(self, host_batch):
         s = self.i % self.depth
-        compute = torch.cuda.current_stream()
+        caller = torch.cuda.current_stream()
+        compute = self.compute[s] if self.lanes else caller
+        fwd = self.forward[s] if self.lanes else self.forward
         with torch.cuda.stream(self.h2d):
             self.h2d.wait_event(self.in_free[s])          # the forward that last used this buffer set has read it
             for k, dst in self.slots[s].items():
                 dst.copy_(host_batch[k], non_blocking=True)
             self.in_ready[s].record(self.h2d)
-        compute.wait_event(self.in_ready[s])
-        dev = self.slots[s]
-        out = self.forward(self.prepare(dev) if self.prepare is not None else dev)
-        self.in_free[s].record(compute)
-        if self.out_dev is None:
-            self.out_dev = [torch.empty_like(out) for _ in range(self.depth)]
-            self.out_host = [torch.empty(out.shape, dtype=out.dtype).pin_memory() for _ in range(self.depth)]
-        compute.wait_event(self.out_free[s])              # the download that last used this output buffer has left it
-        self.out_dev[s].copy_(out)
-        self.out_ready[s].record(compute)
+        with torch.cuda.stream(compute):
+            if self.lanes and self.i < self.depth:
+                compute.wait_stream(caller)               # first use of the lane: order after the caller's set-up work
+            compute.wait_event(self.in_ready[s])
+            dev = self.slots[s]
+            out = fwd(self.prepare(dev) if self.prepare is not None else dev)
+            self.in_free[s].record(compute)
+            if self.out_dev[s] is None:
+                self.out_dev[s] = torch.empty_like(out)
+                self.out_host[s] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+            compute.wait_event(self.out_free[s])          # the download that last used this output buffer has left it
+            self.out_dev[s].copy_(out)
+            self.out_ready[s].record(compute)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(self.out_ready[s])
             self.out_host[s].copy_(self.out_dev[s], non_blocking=True)
