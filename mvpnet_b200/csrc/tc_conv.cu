@@ -506,25 +506,37 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// device-resident {next, retired} counter pairs for the dynamic work distribution, handed out round-robin per launch;
-// a pair re-arms itself when its launch retires, so only launches 4096 apart in issue order could ever share one
-// (a captured CUDA graph keeps the pairs its launches drew at capture time: two graphs replayed concurrently hold
-// disjoint ranges as long as fewer than 4096 launches were issued between their captures)
-static unsigned int *sched_pair() {
-  constexpr int DEVICES = 64, PAIRS = 4096;
+// Device-resident {next, retired} counter pairs for the dynamic work distribution.  A pair re-arms itself when its
+// launch retires, so it can serve any number of launches that do not overlap in time.
+//   * eager launches draw from a ring of EAGER pairs: two of them could only share a pair with > EAGER launches in flight;
+//   * a launch recorded into a CUDA graph keeps its pair for the lifetime of the graph (the pointer is baked into the
+//     kernel arguments), and graphs may be replayed concurrently with each other and with eager work on other streams:
+//     captured launches therefore take pairs from a separate region that is never handed out again.
+// The pool is allocated on first use; the first use must not be inside a stream capture (cudaMalloc is illegal there) —
+// warm the path up once before capturing, as engine.GraphedForward does.
+static unsigned int *sched_pair(cudaStream_t stream) {
+  constexpr int DEVICES = 64, EAGER = 4096, CAPTURED = 61440;
   static unsigned int *pool[DEVICES] = {};
-  static unsigned int next[DEVICES] = {};
+  static unsigned int next_eager[DEVICES] = {}, next_captured[DEVICES] = {};
   static std::mutex mu;                              // nn.DataParallel calls in from one thread per GPU
   std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= DEVICES) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
   if (pool[dev] == nullptr) {
+    if (cap != cudaStreamCaptureStatusNone) return nullptr;
     unsigned int *p = nullptr;
-    if (cudaMalloc(&p, PAIRS * 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(p, 0, PAIRS * 2 * sizeof(unsigned int)) != cudaSuccess) return nullptr;
+    const size_t bytes = (size_t)(EAGER + CAPTURED) * 2 * sizeof(unsigned int);
+    if (cudaMalloc(&p, bytes) != cudaSuccess || cudaMemset(p, 0, bytes) != cudaSuccess) return nullptr;
     pool[dev] = p;
   }
-  return pool[dev] + 2 * (next[dev]++ % PAIRS);
+  if (cap != cudaStreamCaptureStatusNone) {
+    if (next_captured[dev] >= (unsigned)CAPTURED) return nullptr;      // 61440 captured launches per process and device
+    return pool[dev] + 2 * ((size_t)EAGER + next_captured[dev]++);
+  }
+  return pool[dev] + 2 * (size_t)(next_eager[dev]++ % EAGER);
 }
 
 // tensor map over one plane of a split-planar activation tensor; box = one tile's patch of one 16-channel chunk
@@ -657,8 +669,9 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   if (e != cudaSuccess) { set_error("tc_conv3x3: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;
   MVP_REQUIRE(nworks < (1LL << 30), MVP_ERR_UNSUPPORTED, "tc_conv3x3: too many work items");
-  a.sched = tcc::sched_pair();
-  MVP_REQUIRE(a.sched != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv3x3: could not allocate the scheduler counters");
+  a.sched = tcc::sched_pair((cudaStream_t)stream);
+  MVP_REQUIRE(a.sched != nullptr, MVP_ERR_UNSUPPORTED,
+              "tc_conv3x3: no scheduler counters (first call inside a stream capture, or more than 61440 captured launches)");
   long long grid = sm_count();              // persistent, one CTA per SM
   if (grid > nworks) grid = nworks;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;

@@ -449,8 +449,9 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   if (e != cudaSuccess) { set_error("tc_conv_general: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;
   MVP_REQUIRE(nworks < (1LL << 30), MVP_ERR_UNSUPPORTED, "tc_conv_general: too many work items");
-  a.sched = tcc::sched_pair();
-  MVP_REQUIRE(a.sched != nullptr, MVP_ERR_UNSUPPORTED, "tc_conv_general: could not allocate the scheduler counters");
+  a.sched = tcc::sched_pair((cudaStream_t)stream);
+  MVP_REQUIRE(a.sched != nullptr, MVP_ERR_UNSUPPORTED,
+              "tc_conv_general: no scheduler counters (first call inside a stream capture, or more than 61440 captured launches)");
   long long grid = sm_count();
   if (grid > nworks) grid = nworks;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
