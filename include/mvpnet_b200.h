@@ -213,6 +213,23 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
                                      const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
                                      const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream);
 
+/* ==== second-generation fused gather kernels (csrc/tc2_mlp.cu): PRE-SPLIT inputs =====================
+ * Same arithmetic and chain format as mvp_tc_fused_set_abstraction / _feature_aggregation, but the gathered
+ * features arrive as two bf16 planes (hi = bf16(v), lo = bf16(v - hi)), rows of C = 64 / 128 / 256 channels
+ * (feat_hi / feat_lo [B*N, C]; pix_hi / pix_lo [(B*nv), hp, wp, C] with hp >= h, wp >= w the padded image the 2D
+ * network writes), are staged by cp.async straight into the swizzled MMA operand layout, inner layers keep their
+ * activations in tensor memory, and the result is written fp32 (out_f32 [rows, out_channels], may be NULL) and / or
+ * pre-split for the next gather (out_hi / out_lo, both or neither).  k[0] must be C + 16, every n <= 256, all weights
+ * resident in shared memory: mvp_tc2_supported() tells; callers fall back to the mvp_tc_fused_* entry otherwise. */
+int mvp_tc2_supported(const mvp_tc_chain_t *chain, int mode, int64_t C);
+int mvp_tc2_set_abstraction(const void *feat_hi, const void *feat_lo, int64_t C, const float *xyz, const float *new_xyz,
+                            const int64_t *nbr, int64_t B, int64_t N, int64_t M, int64_t K, const mvp_tc_chain_t *chain,
+                            float *out_f32, void *out_hi, void *out_lo, mvp_stream_t stream);
+int mvp_tc2_feature_aggregation(const void *pix_hi, const void *pix_lo, int64_t C, int64_t nv, int64_t h, int64_t w,
+                                int64_t hp, int64_t wp, const float *pix_xyz, const float *points, const int64_t *knn,
+                                int64_t B, int64_t Np, int64_t K, int reduce_sum, const mvp_tc_chain_t *chain,
+                                float *out_f32, void *out_hi, void *out_lo, mvp_stream_t stream);
+
 /* ==== 3x3 / stride 1 / pad 1 convolution on the tensor cores (csrc/tc_conv.cu) ========================
  * The convolutions of the 2D network in front of FeatureAggregation (mvpnet/models/unet_resnet34.py:9-125;
  * called from MVPNet3D.forward, mvpnet_3d.py:94-99):
@@ -222,7 +239,8 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
  * [ceil(N/2)][C/8][H][2][W][8] (image 2p and 2p+1 share rows; a missing partner must read as zeros).
  * mvp_planar_elems() gives the bf16 element count of both planes; mvp_split_planar / mvp_merge_planar convert from /
  * to fp32 NHWC.  x2 may be NULL (C2 = 0): cat([up, skip]) without the copy.  residual (split-planar, Cout channels)
- * may be NULL.  The result is written split-planar (out_planar) and / or as fp32 NHWC (out_nhwc); at least one.
+ * may be NULL.  The result is written split-planar (out_planar), as fp32 NHWC (out_nhwc) and / or row-split (out_rows:
+ * two bf16 planes hi, then lo, each NHWC — the pre-split pixel rows mvp_tc2_feature_aggregation gathers); at least one.
  * C1, C2, Cout multiples of 16 (Cout a multiple of Nt above it).  Weights (BatchNorm folded by the caller) are
  * split the same way and stored in the kernel's operand order [Cout/Nt][Cin/16][tap = ky*3+kx][hi|lo][2][Nt][8],
  * Nt = mvp_tc_conv3x3_nt(Cout) (= min(Cout, 256)), element (nb, c, tap, hl, k8, n, e) = W_hl[nb*Nt + n, c*16 + k8*8 + e, ky, kx]:
@@ -232,7 +250,7 @@ int64_t mvp_tc_conv3x3_nt(int64_t Cout);
 int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C);
 int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
                    const void *w_packed, const float *bias, int64_t Cout, const void *residual, int relu,
-                   void *out_planar, float *out_nhwc, mvp_stream_t stream);
+                   void *out_planar, float *out_nhwc, void *out_rows, mvp_stream_t stream);
 int mvp_split_planar(const float *nhwc, int64_t N, int64_t H, int64_t W, int64_t C, void *planar, mvp_stream_t stream);
 int mvp_merge_planar(const void *planar, int64_t N, int64_t H, int64_t W, int64_t C, float *nhwc, mvp_stream_t stream);
 

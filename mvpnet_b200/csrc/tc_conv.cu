@@ -58,6 +58,7 @@ struct ConvArgs {
   const __nv_bfloat16 *res;         // split-planar residual (hi plane; lo at + plane_out) or null
   __nv_bfloat16 *out_p;             // split-planar output or null
   float *out_f;                     // fp32 NHWC output or null
+  __nv_bfloat16 *out_rh, *out_rl;   // row-split output or null: bf16 hi / lo planes, each NHWC (one 2*Cout-byte row per pixel)
   long long plane_out;              // elements of one plane of res / out_p
   int Cout, Nt, NB;
   int relu;
@@ -290,6 +291,14 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
               float4 *op = reinterpret_cast<float4 *>(a.out_f + cur.fbase + c);
 #pragma unroll
               for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (a.out_rh != nullptr) {   // what the fused FeatureAggregation gathers: pixel-major rows, already split
+              uint32_t h[8], l[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
+              uint4 *oh = reinterpret_cast<uint4 *>(a.out_rh + cur.fbase + c), *ol = reinterpret_cast<uint4 *>(a.out_rl + cur.fbase + c);
+              oh[0] = make_uint4(h[0], h[1], h[2], h[3]); oh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              ol[0] = make_uint4(l[0], l[1], l[2], l[3]); ol[1] = make_uint4(l[4], l[5], l[6], l[7]);
             }
           }
         }
@@ -587,7 +596,7 @@ extern "C" int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C) 
 
 extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
                               const void *w_packed, const float *bias, int64_t Cout, const void *residual, int relu,
-                              void *out_planar, float *out_nhwc, mvp_stream_t stream) {
+                              void *out_planar, float *out_nhwc, void *out_rows, mvp_stream_t stream) {
   using namespace mvp;
   MVP_REQUIRE(N >= 0 && H > 0 && W > 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: bad sizes");
   MVP_REQUIRE(C1 > 0 && C1 % 16 == 0 && C2 >= 0 && C2 % 16 == 0, MVP_ERR_UNSUPPORTED, "tc_conv3x3: input channels must be multiples of 16");
@@ -595,9 +604,9 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
               "tc_conv3x3: output channels must be a multiple of 16, and of the block width mvp_tc_conv3x3_nt() above it");
   MVP_REQUIRE(N * H * W < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv3x3: more than 2^31 pixels");
   if (N == 0) return 0;
-  MVP_REQUIRE(x1 && w_packed && bias && (out_planar || out_nhwc) && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3: null pointer");
+  MVP_REQUIRE(x1 && w_packed && bias && (out_planar || out_nhwc || out_rows) && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3: null pointer");
   MVP_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)out_planar |
-                (uintptr_t)out_nhwc) & 15) == 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: pointers must be 16-byte aligned");
+                (uintptr_t)out_nhwc | (uintptr_t)out_rows) & 15) == 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: pointers must be 16-byte aligned");
   tcc::ConvArgs a = {};
   const int pair = H <= 8 ? 1 : 0;
   const int64_t Np = pair ? (N + 1) / 2 * 2 : N;
@@ -609,7 +618,8 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   }
   a.C1 = (int)C1; a.C2 = (int)C2; a.N = (int)N; a.H = (int)H; a.W = (int)W;
   a.wp = (const unsigned char *)w_packed; a.bias = bias; a.res = (const __nv_bfloat16 *)residual;
-  a.out_p = (__nv_bfloat16 *)out_planar; a.out_f = out_nhwc; a.plane_out = Np * Cout * H * W; a.relu = relu;
+  a.out_p = (__nv_bfloat16 *)out_planar; a.out_f = out_nhwc;
+  a.out_rh = (__nv_bfloat16 *)out_rows; a.out_rl = out_rows ? (__nv_bfloat16 *)out_rows + N * H * W * Cout : nullptr; a.plane_out = Np * Cout * H * W; a.relu = relu;
   a.Cout = (int)Cout; a.Nt = (int)mvp_tc_conv3x3_nt(Cout); a.NB = a.Cout / a.Nt;
   a.ipt = pair ? 2 : 1;
   a.TX = (int)((W + 7) / 8);

@@ -422,7 +422,8 @@ at::Tensor merge_planar(const at::Tensor planar, int64_t N, int64_t H, int64_t W
 // x1 (C1 channels) [+ x2 (C2 channels)] split-planar, packed weights, bias (Cout), optional split-planar residual
 // -> split-planar (N,H,W,Cout), or fp32 NHWC when nhwc_out
 at::Tensor tc_conv3x3(const at::Tensor x1, int64_t C1, const c10::optional<at::Tensor> x2, int64_t C2, int64_t N, int64_t H, int64_t W,
-                      const at::Tensor w_packed, const at::Tensor bias, const c10::optional<at::Tensor> residual, bool relu, bool nhwc_out) {
+                      const at::Tensor w_packed, const at::Tensor bias, const c10::optional<at::Tensor> residual, bool relu, int64_t out_mode) {
+  // out_mode 0: split-planar; 1: fp32 NHWC; 2: row-split (2, N, H, W, Cout) bf16 (hi plane, lo plane)
   CHECK_INPUT(x1); CHECK_INPUT(w_packed); CHECK_INPUT(bias); CHECK_F32(bias);
   const auto Cout = bias.size(0);
   TORCH_CHECK(x1.scalar_type() == at::kBFloat16 && x1.numel() == mvp_planar_elems(N, H, W, C1), "tc_conv3x3: x1 is not split-planar (N,H,W,C1)");
@@ -444,15 +445,19 @@ at::Tensor tc_conv3x3(const at::Tensor x1, int64_t C1, const c10::optional<at::T
               "tc_conv3x3: packed weights have the wrong size for ", C1 + C2, " -> ", Cout, " channels");
   c10::cuda::CUDAGuard guard(x1.device());
   at::Tensor out;
-  if (nhwc_out) {
+  if (out_mode == 1) {
     out = at::empty({N, H, W, Cout}, x1.options().dtype(at::kFloat));
     check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
-                            nullptr, out.data_ptr<float>(), cur_stream()));
+                            nullptr, out.data_ptr<float>(), nullptr, cur_stream()));
+  } else if (out_mode == 2) {
+    out = at::empty({2, N, H, W, Cout}, x1.options());
+    check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
+                            nullptr, nullptr, out.data_ptr(), cur_stream()));
   } else {
     // an odd image count leaves a partner-less image in the last pair of a pair-interleaved tensor: keep it zero
     out = (H <= 8 && (N & 1)) ? at::zeros({mvp_planar_elems(N, H, W, Cout)}, x1.options()) : at::empty({mvp_planar_elems(N, H, W, Cout)}, x1.options());
     check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
-                            out.data_ptr(), nullptr, cur_stream()));
+                            out.data_ptr(), nullptr, nullptr, cur_stream()));
   }
   return out;
 }
@@ -531,6 +536,79 @@ at::Tensor tc_set_abstraction(const c10::optional<at::Tensor> feat, const at::Te
   check_rc(mvp_tc_fused_set_abstraction(fp, C, xyz.data_ptr<float>(), new_xyz.data_ptr<float>(), nbr.data_ptr<int64_t>(), B, N, M,
                                         K, &ch.c, out.data_ptr<float>(), cur_stream()));
   return out;
+}
+
+// ---- second-generation kernels (csrc/tc2_mlp.cu): features travel pre-split as one bf16 tensor (2, ..., C) = (hi, lo)
+bool tc2_supported(const std::vector<int64_t> ks, const std::vector<int64_t> ns, int64_t mode, int64_t C) {
+  mvp_tc_chain_t c = {};
+  if (ks.empty() || ks.size() > MVP_MLP_MAX_LAYERS || ks.size() != ns.size()) return false;
+  c.num_layers = (int32_t)ks.size();
+  for (size_t l = 0; l < ks.size(); ++l) { c.k[l] = (int32_t)ks[l]; c.n[l] = (int32_t)ns[l]; }
+  c.out_channels = c.n[c.num_layers - 1];
+  return mvp_tc2_supported(&c, (int)mode, C) != 0;
+}
+
+static void check_split(const at::Tensor &t, const char *what) {
+  TORCH_CHECK(t.is_cuda() && t.is_contiguous() && t.scalar_type() == at::kBFloat16 && t.dim() >= 3 && t.size(0) == 2, what,
+              " must be a contiguous CUDA bfloat16 tensor (2, ..., C): hi plane, lo plane");
+}
+
+// returns (out_f32 (B, M, oc) or an empty tensor, out_split (2, B, M, oc) or an empty tensor)
+std::tuple<at::Tensor, at::Tensor> tc2_set_abstraction(const at::Tensor feat_split, const at::Tensor xyz, const at::Tensor new_xyz,
+                                                       const at::Tensor nbr, const std::vector<at::Tensor> w_hi, const std::vector<at::Tensor> w_lo,
+                                                       const std::vector<at::Tensor> biases, const std::vector<int64_t> ks,
+                                                       const std::vector<int64_t> ns, const std::vector<int64_t> relu, int64_t out_channels,
+                                                       bool want_f32, bool want_split) {
+  CHECK_INPUT(xyz); CHECK_INPUT(new_xyz); CHECK_INPUT(nbr);
+  CHECK_F32(xyz); CHECK_F32(new_xyz);
+  check_split(feat_split, "feat_split");
+  TORCH_CHECK(xyz.dim() == 3 && xyz.size(2) == 3 && new_xyz.dim() == 3 && new_xyz.size(2) == 3, "xyz/new_xyz must be (B, N, 3)");
+  TORCH_CHECK(nbr.scalar_type() == at::kLong && nbr.dim() == 3, "nbr must be int64 (B, M, K)");
+  const auto B = xyz.size(0), N = xyz.size(1), M = new_xyz.size(1), K = nbr.size(2);
+  TORCH_CHECK(new_xyz.size(0) == B && nbr.size(0) == B && nbr.size(1) == M, "tc2_set_abstraction: shape mismatch");
+  TORCH_CHECK(feat_split.dim() == 4 && feat_split.size(1) == B && feat_split.size(2) == N, "feat_split must be (2, B, N, C)");
+  TORCH_CHECK(want_f32 || want_split, "tc2_set_abstraction: no output requested");
+  const auto C = feat_split.size(3);
+  c10::cuda::CUDAGuard guard(xyz.device());
+  TcChain ch(w_hi, w_lo, biases, ks, ns, relu, out_channels, xyz.device());
+  at::Tensor out = want_f32 ? at::empty({B, M, out_channels}, xyz.options()) : at::empty({0}, xyz.options());
+  at::Tensor sp = want_split ? at::empty({2, B, M, out_channels}, feat_split.options()) : at::empty({0}, feat_split.options());
+  const auto *fh = (const at::BFloat16 *)feat_split.data_ptr();
+  auto *oh = want_split ? (at::BFloat16 *)sp.data_ptr() : nullptr;
+  check_rc(mvp_tc2_set_abstraction(fh, fh + B * N * C, C, xyz.data_ptr<float>(), new_xyz.data_ptr<float>(), nbr.data_ptr<int64_t>(), B, N, M, K,
+                                   &ch.c, want_f32 ? out.data_ptr<float>() : nullptr, oh, oh ? oh + B * M * out_channels : nullptr, cur_stream()));
+  return std::make_tuple(out, sp);
+}
+
+// pix_split (2, B*nv, hp, wp, C): the row-split output of the 2D network (padded image geometry)
+std::tuple<at::Tensor, at::Tensor> tc2_feature_aggregation(const at::Tensor pix_split, int64_t nv, int64_t h, int64_t w, const at::Tensor pix_xyz,
+                                                           const at::Tensor points, const at::Tensor knn, bool reduce_sum,
+                                                           const std::vector<at::Tensor> w_hi, const std::vector<at::Tensor> w_lo,
+                                                           const std::vector<at::Tensor> biases, const std::vector<int64_t> ks,
+                                                           const std::vector<int64_t> ns, const std::vector<int64_t> relu, int64_t out_channels,
+                                                           bool want_f32, bool want_split) {
+  CHECK_INPUT(pix_xyz); CHECK_INPUT(points); CHECK_INPUT(knn);
+  CHECK_F32(pix_xyz); CHECK_F32(points);
+  check_split(pix_split, "pix_split");
+  TORCH_CHECK(pix_split.dim() == 5, "pix_split must be (2, B*nv, hp, wp, C)");
+  const auto hp = pix_split.size(2), wp = pix_split.size(3), C = pix_split.size(4);
+  TORCH_CHECK(nv > 0 && pix_split.size(1) % nv == 0 && hp >= h && wp >= w, "tc2_feature_aggregation: image geometry mismatch");
+  const auto B = pix_split.size(1) / nv;
+  TORCH_CHECK(pix_xyz.dim() == 3 && pix_xyz.size(0) == B && pix_xyz.size(1) == nv * h * w && pix_xyz.size(2) == 3, "pix_xyz must be (B, nv*h*w, 3)");
+  TORCH_CHECK(points.dim() == 3 && points.size(0) == B && points.size(2) == 3, "points must be (B, Np, 3)");
+  TORCH_CHECK(knn.scalar_type() == at::kLong && knn.dim() == 3 && knn.size(0) == B && knn.size(1) == points.size(1), "knn must be int64 (B, Np, K)");
+  TORCH_CHECK(want_f32 || want_split, "tc2_feature_aggregation: no output requested");
+  const auto Np = points.size(1);
+  c10::cuda::CUDAGuard guard(points.device());
+  TcChain ch(w_hi, w_lo, biases, ks, ns, relu, out_channels, points.device());
+  at::Tensor out = want_f32 ? at::empty({B, Np, out_channels}, points.options()) : at::empty({0}, points.options());
+  at::Tensor sp = want_split ? at::empty({2, B, Np, out_channels}, pix_split.options()) : at::empty({0}, pix_split.options());
+  const auto *ph = (const at::BFloat16 *)pix_split.data_ptr();
+  auto *oh = want_split ? (at::BFloat16 *)sp.data_ptr() : nullptr;
+  check_rc(mvp_tc2_feature_aggregation(ph, ph + pix_split.numel() / 2, C, nv, h, w, hp, wp, pix_xyz.data_ptr<float>(), points.data_ptr<float>(),
+                                       knn.data_ptr<int64_t>(), B, Np, knn.size(2), reduce_sum ? 1 : 0, &ch.c,
+                                       want_f32 ? out.data_ptr<float>() : nullptr, oh, oh ? oh + B * Np * out_channels : nullptr, cur_stream()));
+  return std::make_tuple(out, sp);
 }
 
 at::Tensor tc_feature_aggregation(const at::Tensor feat2d, const at::Tensor pix_xyz, const at::Tensor points, const at::Tensor knn,
@@ -623,6 +701,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("feature_propagation", &fused_feature_propagation, "3-NN interpolate + concat + MLP (CUDA)");
   fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
   fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
+  fz.def("tc2_supported", &tc2_supported, "does the chain fit the pre-split-input tcgen05 kernel (csrc/tc2_mlp.cu)");
+  fz.def("tc2_set_abstraction", &tc2_set_abstraction, "pre-split gather (cp.async, swizzled operand) + MLP (tcgen05, TMEM activations) + max");
+  fz.def("tc2_feature_aggregation", &tc2_feature_aggregation, "pre-split pixel gather + relation + MLP (tcgen05, TMEM activations) + reduce over k");
   fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv on split-planar activations, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
   fz.def("tc_conv3x3_nt", &mvp_tc_conv3x3_nt, "output-channel block width of the packed 3x3 weights");
   fz.def("tc_conv_general", &tc_conv_general, "tap-staged conv / 2x2 transposed conv on split-planar activations (tcgen05)");

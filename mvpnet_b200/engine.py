@@ -160,6 +160,19 @@ MLP_BACKEND = os.environ.get('MVPNET_B200_MLP', 'tc')
 # 64 strided channels per pixel straight from the NCHW output of the 2D network
 FA_CHANNELS_LAST_COPY = os.environ.get('MVPNET_B200_FA_CHANNELS_LAST_COPY', '0') == '1'
 _MODE_SA, _MODE_FA, _MODE_FP = 0, 1, 2
+# second-generation kernels (csrc/tc2_mlp.cu: pre-split inputs, cp.async gather into the swizzled operand, activations in
+# tensor memory) where the chain fits them; '0' keeps every chain on csrc/tc_mlp.cu (cross-check)
+TC2 = os.environ.get('MVPNET_B200_TC2', '1') == '1'
+
+
+def split_rows(x):
+    """fp32 (..., C) -> bf16 (2, ..., C): hi = bf16(x), lo = bf16(x - hi) — the pre-split row format of the tc2 kernels."""
+    hi = x.bfloat16()
+    return torch.stack([hi, (x - hi.float()).bfloat16()])
+
+
+def _tc2_ok(chain, mode, c):
+    return TC2 and isinstance(chain, TcChain) and c > 0 and load_ext().fused_cuda.tc2_supported(chain.ks, chain.ns, mode, c)
 
 
 def _make_chain(layers, cin_true, device, mode, channels_ok):
@@ -203,6 +216,27 @@ def _require_eval_fp32(module, *tensors):
 # ------------------------------------------------------------------------------------------------
 # FeatureAggregation
 # ------------------------------------------------------------------------------------------------
+def feature_aggregation_rows(fa, pix_split, nv, h, w, image_xyz, knn_indices, points, want_f32=False, want_split=True):
+    """FeatureAggregation on the PRE-SPLIT pixel rows of the 2D network (net2d.FastUNetResNet34.features_rows:
+    bf16 (2, b*nv, hp, wp, c)).  Returns (out fp32 (b, np, c_out) or None, out_split bf16 (2, b, np, c_out) or None),
+    or None when the chain does not fit the tc2 kernel (caller falls back to feature_aggregation())."""
+    ext = load_ext()
+    _require_eval_fp32(fa, image_xyz, points)
+    if fa.mlp is None or not fa.use_relation or knn_indices.size(2) > 4:
+        return None
+    c = pix_split.size(-1)
+    chain = _cached(fa, 'fa' + MLP_BACKEND, lambda: _make_chain(_mlp_layers(fa.mlp), c + 4, points.device, _MODE_FA, c % 8 == 0))
+    if not _tc2_ok(chain, _MODE_FA, c):
+        return None
+    b = points.size(0)
+    pix = image_xyz.reshape(b, nv * h * w, 3).contiguous()
+    pts = points.transpose(1, 2).contiguous()
+    with _stage('feature_aggregation'):
+        out, sp = ext.fused_cuda.tc2_feature_aggregation(pix_split, nv, h, w, pix, pts, knn_indices.contiguous(), fa.reduction_name == 'sum',
+                                                         *chain.args(), want_f32, want_split)
+    return (out if want_f32 else None), (sp if want_split else None)
+
+
 def feature_aggregation(fa, feat2d, image_xyz, knn_indices, points, point_major_out=False):
     """fa: FeatureAggregation module (eval).  feat2d (b, nv, c, h, w) — the 2D network output viewed per
     chunk, any memory format; image_xyz (b, nv, h, w, 3); knn_indices (b, np, k); points (b, 3, np).
@@ -275,20 +309,33 @@ def _pn2_chains(net, device):
     return sa, fp
 
 
-def pn2_features(net, geo, feature_pm):
-    """The feature side of PN2SSG.forward on precomputed geometry.  feature_pm (B, N, C) or None.
-    Returns seg_logit (B, num_classes, N)."""
+def pn2_features(net, geo, feature_pm, feature_split=None):
+    """The feature side of PN2SSG.forward on precomputed geometry.  feature_pm (B, N, C) fp32 or None and / or
+    feature_split bf16 (2, B, N, C) (the pre-split rows a tc2 producer wrote).  Returns seg_logit (B, num_classes, N)."""
     ext = load_ext()
     sa_chains, fp_chains = _cached(net, 'pn2' + MLP_BACKEND, lambda: _pn2_chains(net, geo['xyz'][0].device))
     if len(fp_chains[-1].relu) > 6:
         raise RuntimeError('fused PN2SSG: last FP chain + head exceeds 6 layers')
+    # which SA levels run on the tc2 kernel: their input channel count (without xyz) must be 64 / 128 / 256
+    cin = [(sa.in_channels - 3) if sa.use_xyz else sa.in_channels for sa in net.sa_modules]
+    use2 = [_tc2_ok(sa_chains[i], _MODE_SA, cin[i]) and (i > 0 or feature_pm is not None or feature_split is not None)
+            for i in range(len(net.sa_modules))]
     feats = [None]
-    f = feature_pm
+    f, fs = feature_pm, feature_split
     for i, sa in enumerate(net.sa_modules):
-        src = f if (f is not None) else None
-        fn = ext.fused_cuda.tc_set_abstraction if isinstance(sa_chains[i], TcChain) else ext.fused_cuda.set_abstraction
         with _stage('set_abstraction%d' % (i + 1)):
-            f = fn(src, geo['xyz'][i], geo['xyz'][i + 1], geo['nbr'][i], *sa_chains[i].args())
+            if use2[i]:
+                if fs is None:
+                    fs = split_rows(f)
+                want_split = i + 1 < len(use2) and use2[i + 1]
+                f, fs = ext.fused_cuda.tc2_set_abstraction(fs, geo['xyz'][i], geo['xyz'][i + 1], geo['nbr'][i], *sa_chains[i].args(),
+                                                           True, want_split)
+                fs = fs if want_split else None
+            else:
+                if f is None and fs is not None:          # only reachable with a caller-supplied split input
+                    f = fs[0].float() + fs[1].float()
+                fn = ext.fused_cuda.tc_set_abstraction if isinstance(sa_chains[i], TcChain) else ext.fused_cuda.set_abstraction
+                f, fs = fn(f, geo['xyz'][i], geo['xyz'][i + 1], geo['nbr'][i], *sa_chains[i].args()), None
         feats.append(f)
     x = feats[-1]
     for i, fp in enumerate(net.fp_modules):
@@ -407,19 +454,29 @@ def mvpnet3d_forward(model, data_batch, overlap=True):
             rg, geo = coordinate_work()
     else:
         rg, geo = coordinate_work()
+    fa = model.feat_aggreg
+    fa_chain = _cached(fa, 'fa' + MLP_BACKEND, lambda: _make_chain(_mlp_layers(fa.mlp), 64 + 4, images.device, _MODE_FA, True)) \
+        if fa.in_channels == 64 else None
     with _stage('net_2d'):
         plan = _tc_net2d(model.net_2d)
-        if plan is not None:      # tcgen05 convolutions, fp32 NHWC end to end; (n, c, h, w) view with channel stride 1
+        rows = plan is not None and fa_chain is not None and _tc2_ok(fa_chain, _MODE_FA, 64)
+        if rows:                  # tcgen05 convolutions; the last one writes pre-split pixel rows for the tc2 gather
+            pix_split = plan.features_rows(images.reshape(b * nv, *images.shape[2:]))
+        elif plan is not None:    # tcgen05 convolutions, fp32 NHWC end to end; (n, c, h, w) view with channel stride 1
             feat2d = plan.features_nhwc(images.reshape(b * nv, *images.shape[2:])).permute(0, 3, 1, 2)
         else:
             feat2d = _folded_net2d(model.net_2d).features(images.reshape(b * nv, *images.shape[2:]))
-    if FA_CHANNELS_LAST_COPY and feat2d.stride(1) != 1:
-        with _stage('feat2d_to_channels_last'):
-            feat2d = feat2d.contiguous(memory_format=torch.channels_last)   # one pass; pixel rows become 256-byte lines
-    feat2d = feat2d.view(b, nv, *feat2d.shape[1:])
+    if not rows:
+        if FA_CHANNELS_LAST_COPY and feat2d.stride(1) != 1:
+            with _stage('feat2d_to_channels_last'):
+                feat2d = feat2d.contiguous(memory_format=torch.channels_last)   # one pass; pixel rows become 256-byte lines
+        feat2d = feat2d.view(b, nv, *feat2d.shape[1:])
     if overlap:
         main.wait_stream(side)
-    fa_pm = feature_aggregation(model.feat_aggreg, feat2d, rg['image_xyz'], rg['knn_indices'], points, point_major_out=True)
+    if rows:
+        _, fa_split = feature_aggregation_rows(fa, pix_split, nv, h, w, rg['image_xyz'], rg['knn_indices'], points)
+        return {'seg_logit': pn2_features(net3d, geo, None, fa_split)}
+    fa_pm = feature_aggregation(fa, feat2d, rg['image_xyz'], rg['knn_indices'], points, point_major_out=True)
     return {'seg_logit': pn2_features(net3d, geo, fa_pm)}
 
 

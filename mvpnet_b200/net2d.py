@@ -110,16 +110,16 @@ def _stage(name):
     return engine._stage(name)
 
 
-def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=False):
+def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=0):
     """x1 [, x2]: Planar inputs (concatenated along channels); residual: Planar or None.
-    Returns a Planar, or an fp32 (N, H, W, Cout) tensor when nhwc_out."""
+    Returns a Planar; nhwc_out=1: an fp32 (N, H, W, Cout) tensor; nhwc_out=2: row-split (2, N, H, W, Cout) bf16 (hi, lo planes)."""
     with _stage('net_2d/conv3x3'):
         return _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out)
 
 
 def _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out):
     out = load_ext().fused_cuda.tc_conv3x3(x1.data, x1.c, None if x2 is None else x2.data, 0 if x2 is None else x2.c,
-                                           x1.n, x1.h, x1.w, packed, bias, None if residual is None else residual.data, relu, nhwc_out)
+                                           x1.n, x1.h, x1.w, packed, bias, None if residual is None else residual.data, relu, int(nhwc_out))
     return out if nhwc_out else Planar(out, x1.n, x1.h, x1.w, bias.numel())
 
 
@@ -173,8 +173,18 @@ class FastUNetResNet34:
             self.dec.append({'up': pack_deconv2x2(*fold_conv_bn(up[0], up[1])), 'fuse': pack_conv3x3(*fold_conv_bn(fuse[0], fuse[1]))})
 
     @torch.no_grad()
+    def features_rows(self, x):
+        """image (n,3,h,w) fp32 -> the 64-channel feature map as PRE-SPLIT pixel rows: bf16 (2, n, hp, wp, 64) = (hi, lo)
+        planes over the padded image (hp, wp multiples of 16) — what mvp_tc2_feature_aggregation gathers."""
+        return self._run(x, 2)
+
+    @torch.no_grad()
     def features_nhwc(self, x):
         """image (n,3,h,w) fp32 -> 64-channel feature map (n, h, w, 64) fp32, a view of the (padded) NHWC output."""
+        n, _, h, w = x.shape
+        return self._run(x, 1)[:, :h, :w, :]
+
+    def _run(self, x, out_mode):
         n, _, h, w = x.shape
         pad_h, pad_w = (-h) % 16, (-w) % 16
         if pad_h or pad_w:
@@ -198,5 +208,5 @@ class FastUNetResNet34:
             if li < 3:
                 skips.append(x)
         for i, (d, skip) in enumerate(zip(self.dec, (skips[3], skips[2], skips[1], skips[0]))):
-            x = conv3x3(deconv2x2(x, *d['up'], relu=True), *d['fuse'], x2=skip, relu=True, nhwc_out=(i == 3))
-        return x[:, :h, :w, :]
+            x = conv3x3(deconv2x2(x, *d['up'], relu=True), *d['fuse'], x2=skip, relu=True, nhwc_out=(out_mode if i == 3 else 0))
+        return x

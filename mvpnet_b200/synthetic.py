@@ -153,6 +153,22 @@ def make_chunk(seed=0, num_points=8192, num_views=5, h=120, w=160, drop=0.1, can
             'cam_matrix': cam, 'pose': np.stack(poses), 'images': images, 'chunk_box': box}
 
 
+def train_batch(batch, num_points=8192, channels=64, num_classes=20):
+    """Seeded inputs of one training step (BASELINE config 2 / SURVEY §8 f4): room chunks (b, n, 3), features
+    (b, c, n) ~ N(0, 1), labels (b, n) in [0, num_classes) from a coarse spatial grid with 10 % ignore_index (-100),
+    class weights (num_classes,).  Returns (points ndarray, feature Tensor, label LongTensor, weight Tensor)."""
+    import torch
+    pts = np.stack([room_points(num_points, seed=100 + s)[0] for s in range(batch)])
+    g = torch.Generator().manual_seed(1000 + batch)
+    feat = torch.randn(batch, channels, num_points, generator=g)
+    cell = np.floor(pts / np.array([0.5, 0.5, 0.6], np.float32)).astype(np.int64)
+    label = (cell[..., 0] + 4 * cell[..., 1] + 7 * cell[..., 2]) % num_classes
+    rng = np.random.RandomState(2000 + batch)
+    label[rng.rand(batch, num_points) < 0.1] = -100
+    weight = torch.linspace(0.5, 1.5, num_classes)
+    return pts, feat, torch.from_numpy(label), weight
+
+
 def fill_parameters(module, seed=0):
     """Deterministic, init-order-independent parameters and NON-TRIVIAL BatchNorm statistics, keyed by
     state_dict name, so two implementations of the same architecture get identical weights."""

@@ -67,6 +67,18 @@ def test_fps_room_and_ties(ext):
     assert (ext.fps_cuda.farthest_point_sample(cu(same), 16).cpu().numpy() == 0).all()
 
 
+@pytest.mark.parametrize('n', [100, 300, 1000, 1024, 2048, 3000, 4096, 8192])
+@pytest.mark.parametrize('q', [4, 20])
+def test_fps_tie_order_vs_oracle(ext, n, q):
+    """Exact ties at every launch geometry (N = 1024 / 2048 / 3000 were the round-1 hole), M = N / 2."""
+    rng = np.random.RandomState(n + q)
+    pts = np.round(rng.rand(2, n, 3).astype(np.float32) * 2.0 * q) / q
+    pts[:, n // 2:n // 2 * 2] = pts[:, :n // 2]
+    want = oracle.farthest_point_sample(pts, n // 2)
+    got = ext.fps_cuda.farthest_point_sample(cu(pts), n // 2).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_fps_errors(ext):
     with pytest.raises(RuntimeError):
         ext.fps_cuda.farthest_point_sample(torch.zeros(1, 8, 4).cuda(), 2)

@@ -69,6 +69,31 @@ def test_fps_ties_vs_reference_kernel(ext):
     assert torch.equal(ext.fps_cuda.farthest_point_sample(t, 32), ref.farthest_point_sample(t, 32))
 
 
+def tie_cloud(n, q, seed):
+    """Lattice cloud with heavy exact ties; second half duplicates the first (CropPad-style)."""
+    rng = np.random.RandomState(seed)
+    p = np.round(rng.rand(n, 3).astype(np.float32) * np.array([1.9, 1.9, 2.5], np.float32) * q) / q
+    p[n // 2:n // 2 * 2] = p[:n // 2]
+    return p.astype(np.float32)
+
+
+@pytest.mark.parametrize('n', [300, 1000, 1024, 2048, 3000, 4096, 5000, 8192])
+@pytest.mark.parametrize('q', [4, 8, 20])
+def test_fps_tie_order_all_geometries(ext, n, q):
+    """the reference tie order (bit-reversed thread of a BLOCK = min(2^floor(log2 N), 512)
+    launch, fps_kernel.cu:95-129) at every launch geometry of this package's kernel, M up to N/2, on the
+    reference's own kernel and on the oracle."""
+    ref = load_ref('fps_cuda')
+    pts = np.stack([tie_cloud(n, q, 100 * q + i) for i in range(2)])
+    t = torch.from_numpy(pts).cuda()
+    m = n // 2
+    want = ref.farthest_point_sample(t, m)
+    got = ext.fps_cuda.farthest_point_sample(t, m)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), 'first mismatch at step %d' % int((got != want).any(0).nonzero()[0])
+    assert np.array_equal(oracle.farthest_point_sample(pts, m), want.cpu().numpy())
+
+
 @pytest.mark.parametrize('b,n1,n2,r,k,dtype', [(2, 64, 128, 0.1, 32, torch.float64), (3, 65, 129, 10.0, 32, torch.float64),
                                                (3, 65, 129, 0.1, 32, torch.float32), (4, 512, 1024, 0.1, 64, torch.float32)])
 def test_ball_query_vs_reference_kernel(ext, b, n1, n2, r, k, dtype):
