@@ -213,6 +213,32 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
                                      const float *skip, int64_t Cd, int64_t B, int64_t Ns, int64_t Nd, float eps,
                                      const mvp_tc_chain_t *chain, float *out, mvp_stream_t stream);
 
+/* ==== training step (csrc/train_ops.cu) ================================================
+ * Deterministic backward of group_points / feature_interpolate: same result as mvp_group_points_backward /
+ * mvp_interpolate_backward (reference group_points_kernel.cu:50-89, interpolate_kernel.cu:131-174) but the entries
+ * of every destination point are added in ascending (n, k) order instead of by atomicAdd, so the gradient is the same
+ * bits on every run (fp32 only).  workspace: mvp_scatter_det_workspace_bytes() bytes of device memory. */
+int64_t mvp_scatter_det_workspace_bytes(int64_t B, int64_t C, int64_t N1, int64_t N2, int64_t K, int weighted);
+int mvp_group_points_backward_det(const float *grad_out, const int64_t *index, int64_t B, int64_t C, int64_t N1,
+                                  int64_t N2, int64_t K, float *grad_in, void *workspace, mvp_stream_t stream);
+int mvp_interpolate_backward_det(const float *grad_out, const int64_t *index, const float *weight, int64_t B, int64_t C,
+                                 int64_t N1, int64_t N2, float *grad_in, void *workspace, mvp_stream_t stream);
+/* SegLoss (mvpnet/models/loss.py:5-21): weighted cross entropy over logit [B, C, N] / label [B, N] (int64), mean over
+ * the points whose label != ignore_index, C <= 64.  forward writes loss_out[0] = loss, loss_out[1] = sum of weights,
+ * lse [B*N] (kept for backward) and, when conf != NULL, ADDS the confusion matrix conf[label * C + argmax] (uint64
+ * [C, C]) that SegAccuracy / SegIoU (mvpnet/models/metric.py:26-73) are computed from.  Reductions are two-stage in a
+ * fixed order: deterministic.  workspace: mvp_seg_loss_workspace_bytes() bytes.  backward: grad_logit [B, C, N] =
+ * grad_scale[0] * d loss / d logit.  mvp_seg_confusion: the statistics alone (evaluation). */
+int64_t mvp_seg_loss_workspace_bytes(int64_t B, int64_t N);
+int mvp_seg_loss_forward(const float *logit, const int64_t *label, const float *weight, int64_t B, int64_t C, int64_t N,
+                         int64_t ignore_index, float *lse, float *loss_out, uint64_t *conf, void *workspace,
+                         mvp_stream_t stream);
+int mvp_seg_loss_backward(const float *logit, const int64_t *label, const float *weight, const float *lse,
+                          const float *loss_out, const float *grad_scale, int64_t B, int64_t C, int64_t N,
+                          int64_t ignore_index, float *grad_logit, mvp_stream_t stream);
+int mvp_seg_confusion(const float *logit, const int64_t *label, int64_t B, int64_t C, int64_t N, int64_t ignore_index,
+                      uint64_t *conf, mvp_stream_t stream);
+
 /* ==== second-generation fused gather kernels (csrc/tc2_mlp.cu): PRE-SPLIT inputs =====================
  * Same arithmetic and chain format as mvp_tc_fused_set_abstraction / _feature_aggregation, but the gathered
  * features arrive as two bf16 planes (hi = bf16(v), lo = bf16(v - hi)), rows of C = 64 / 128 / 256 channels
@@ -222,6 +248,7 @@ int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_t Cs, const
  * pre-split for the next gather (out_hi / out_lo, both or neither).  k[0] must be C + 16, every n <= 256, all weights
  * resident in shared memory: mvp_tc2_supported() tells; callers fall back to the mvp_tc_fused_* entry otherwise. */
 int mvp_tc2_supported(const mvp_tc_chain_t *chain, int mode, int64_t C);
+void mvp_tc2_prof_dump(const char *tag);   /* debug: prints the phase clocks collected under MVPNET_B200_TC2_PROF=1 */
 int mvp_tc2_set_abstraction(const void *feat_hi, const void *feat_lo, int64_t C, const float *xyz, const float *new_xyz,
                             const int64_t *nbr, int64_t B, int64_t N, int64_t M, int64_t K, const mvp_tc_chain_t *chain,
                             float *out_f32, void *out_hi, void *out_lo, mvp_stream_t stream);

@@ -49,6 +49,7 @@ struct Args {
   unsigned hw, w, hp_wp, wp, nv;            // FA: pixel j = (v, y, x) of an nv x h x w stack -> feature row (b*nv+v)*hp_wp + y*wp + x
   float *out_f32;                           // [rows_out, out_channels] or null
   __nv_bfloat16 *out_hi, *out_lo;           // [rows_out, out_channels] or null
+  long long *prof;                          // debug (MVPNET_B200_TC2_PROF): per-phase clock64 sums of CTA 0, or null
 };
 
 struct Plan {
@@ -75,6 +76,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -85,6 +87,37 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Worker-side wait: try_wait suspends the warp in hardware instead of spinning.  The fused kernels are issue-bound
+// (ncu: a third of all issued warp instructions were test_wait spins of idle groups), so a waiting group must not
+// compete for issue slots with the groups that have work.  A protocol error traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory"); }
 
 // the group's unit sequence: tiles blockIdx.x + (g + j * NG) * gridDim.x, each `passes` times (FA: one per pixel slot)
@@ -254,15 +287,22 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
       load_xyz(r1, p1, q1);
     }
     uint32_t acc_phase = 0;
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && ltid == 0;
+    long long tp = prof ? clock64() : 0;
+    auto mark = [&](int phase) {
+      if (prof) { const long long t = clock64(); a.prof[g * 16 + phase] += t - tp; tp = t; }
+    };
     for (long long n = 0; n < units; ++n) {
       // ---- layer 0 of unit n: its gather (issued one unit ago) has to have landed
       cp_async_wait_all();
+      mark(0);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_aready);
-      mbar_wait(bar_acc, acc_phase);
+      mbar_wait_sleep(bar_acc, acc_phase);
       acc_phase ^= 1u;
       tc_fence_after();
+      mark(1);
       // ---- the gathered tile is free again: build unit n+1, move the prefetch pipeline one step
       if (c1.valid) build(r1, p1, q1);
       r1 = resolve<MODE>(a, c2, ltid & 127, raw2);
@@ -270,6 +310,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
       const Cursor cur = c0;
       c0 = c1; c1 = c2; c2 = advance(c2);
       raw2 = load_idx(c2);
+      mark(2);
 
       // ---- epilogues: thread = row (TMEM lane 32 * quarter + lane); the two warps of a quarter take alternate 16-column
       //      chunks; the TMEM load of the next chunk is in flight while this one is processed
@@ -366,74 +407,112 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
           c += 2;
         }
         if (last && MODE == MODE_FA) tmem_st_wait();   // the partial columns are re-read by this thread in the next slot
+        mark(3 + 2 * l);
         if (!last) {
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(bar_aready);
-          mbar_wait(bar_acc, acc_phase);
+          mbar_wait_sleep(bar_acc, acc_phase);
           acc_phase ^= 1u;
           tc_fence_after();
+          mark(4 + 2 * l);
         }
       }
     }
     cp_async_wait_all();
   } else {
-    // =========================== MMA issuer (whole warp walks the order, one elected lane issues) ======================
+    // =========================== MMA issuer ===========================================================================
+    // The whole warp polls the groups' request barriers and serves WHICHEVER group is ready (a fixed round-robin order
+    // made the groups advance in lock step: all of them in their epilogues while the tensor pipe idled, then all of
+    // them waiting); every value is warp-uniform, one elected lane issues.
     uint32_t ph[MAXG] = {0u, 0u, 0u};
-    long long units_g[MAXG];
-    long long rounds = 0;
+    int layer[MAXG] = {0, 0, 0};
+    long long left[MAXG] = {0, 0, 0};
+    long long remaining = 0;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      units_g[g] = (n_my > g ? (n_my - g + NG - 1) / NG : 0) * passes;
-      rounds = units_g[g] > rounds ? units_g[g] : rounds;
+      left[g] = (n_my > g ? (n_my - g + NG - 1) / NG : 0) * passes * L;
+      remaining += left[g];
     }
     const uint32_t smem_s = smem_u32(smem), wreg_s = smem_u32(wreg);
-    for (long long r = 0; r < rounds; ++r) {
-      for (int l = 0; l < L; ++l) {
-        const int K = m.k[l], N = m.n[l];
-        const uint32_t idesc = make_idesc(128, N);
-        const uint32_t wh = wreg_s + (uint32_t)m.woff[l], wl = wh + (uint32_t)(K * N * 2);
-        const uint32_t kstep_bytes = (uint32_t)N * 32u;             // 16 channels of the weight operand
+    uint32_t lay_idesc[MAXL], lay_bh[MAXL], lay_bl[MAXL], lay_kinc[MAXL];
+    int lay_ksteps[MAXL];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if (r >= units_g[g]) continue;
-          mbar_wait(bar_aready0 + 8 * g, ph[g]);
-          ph[g] ^= 1u;
-          tc_fence_after();
-          const uint32_t t_acc = tmem_base + (uint32_t)(g * m.tg_cols);
-          if (elect_one()) {
-            if (l == 0) {
-              const uint32_t A_s = smem_s + (uint32_t)g * gbytes;
-              uint32_t ks = 0;
-              for (int qn = 0; qn < m.nchunks; ++qn) {
-                for (int s = 0; s < 4; ++s, ++ks) {
-                  const uint64_t ah = desc_sw128(A_s + (uint32_t)(qn * 2 * CHUNK + s * 32)), al = desc_sw128(A_s + (uint32_t)(qn * 2 * CHUNK + CHUNK + s * 32));
-                  const uint64_t bh = make_desc(wh + ks * kstep_bytes, (uint32_t)N * 16u, 128), bl = make_desc(wl + ks * kstep_bytes, (uint32_t)N * 16u, 128);
-                  umma_bf16(t_acc, ah, bh, idesc, ks != 0u);
-                  umma_bf16(t_acc, ah, bl, idesc, 1u);
-                  umma_bf16(t_acc, al, bh, idesc, 1u);
-                }
+    for (int l = 0; l < MAXL; ++l) {
+      const int K = l < L ? m.k[l] : 16, N = l < L ? m.n[l] : 16;
+      const uint32_t wh = wreg_s + (uint32_t)(l < L ? m.woff[l] : 0), wl = wh + (uint32_t)(K * N * 2);
+      lay_idesc[l] = make_idesc(128, N);
+      lay_bh[l] = ((wh >> 4) & 0x3fffu) | ((uint32_t)N << 16);        // K-direction stride N * 16 bytes (>> 4)
+      lay_bl[l] = ((wl >> 4) & 0x3fffu) | ((uint32_t)N << 16);
+      lay_kinc[l] = (uint32_t)N * 2u;                                  // 16 channels of the weight operand = N * 32 bytes (>> 4)
+      lay_ksteps[l] = K / 16;
+    }
+    uint32_t idle = 0;
+    const bool iprof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    long long ti = iprof ? clock64() : 0;
+    while (remaining > 0) {
+      bool any = false;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (left[g] == 0 || !mbar_test(bar_aready0 + 8 * g, ph[g])) continue;
+        any = true;
+        if (iprof) { const long long t = clock64(); a.prof[48] += t - ti; ti = t; }     // time spent polling
+        ph[g] ^= 1u;
+        tc_fence_after();
+        const int l = layer[g];
+        layer[g] = l + 1 == L ? 0 : l + 1;
+        --left[g];
+        --remaining;
+        // Descriptors as (low word, high word): the low word holds the start address (>> 4) and the K-direction stride,
+        // so stepping to the next K-step / plane / chunk is one 32-bit add.  This warp's instruction stream paces the
+        // narrow layers (an N = 32 MMA is 16 cycles of tensor time): no 64-bit arithmetic, division or descriptor
+        // re-encoding inside the loops (ncu, first version: 40 % of the worker samples were waits on this warp).
+        const uint32_t idesc = lay_idesc[l], b_hi32 = (128u >> 4) | (1u << 14);
+        uint32_t b_h = lay_bh[l], b_l = lay_bl[l];
+        const uint32_t kinc = lay_kinc[l];
+        const uint32_t t_acc = tmem_base + (uint32_t)(g * m.tg_cols);
+        if (elect_one()) {
+          if (l == 0) {
+            constexpr uint32_t a_hi32 = (1024u >> 4) | (1u << 14) | (2u << 29);        // SWIZZLE_128B, 8-row groups 1024 B apart
+            uint32_t a_h = ((smem_s + (uint32_t)g * gbytes) >> 4) | (1u << 16), a_l = a_h + (CHUNK >> 4);
+            uint32_t acc = 0u;
+            for (int qn = 0; qn < m.nchunks; ++qn) {
+#pragma unroll
+              for (int s4 = 0; s4 < 4; ++s4) {
+                umma_bf16(t_acc, desc64(a_h, a_hi32), desc64(b_h, b_hi32), idesc, acc);
+                umma_bf16(t_acc, desc64(a_h, a_hi32), desc64(b_l, b_hi32), idesc, 1u);
+                umma_bf16(t_acc, desc64(a_l, a_hi32), desc64(b_h, b_hi32), idesc, 1u);
+                acc = 1u;
+                a_h += 2u; a_l += 2u; b_h += kinc; b_l += kinc;
               }
-              const uint32_t rel_s = A_s + (uint32_t)(m.nchunks * 2 * CHUNK);
-              const uint64_t ah = make_desc(rel_s, 2048, 128), al = make_desc(rel_s + REL_PLANE, 2048, 128);
-              const uint64_t bh = make_desc(wh + ks * kstep_bytes, (uint32_t)N * 16u, 128), bl = make_desc(wl + ks * kstep_bytes, (uint32_t)N * 16u, 128);
-              umma_bf16(t_acc, ah, bh, idesc, 1u);
-              umma_bf16(t_acc, ah, bl, idesc, 1u);
-              umma_bf16(t_acc, al, bh, idesc, 1u);
-            } else {
-              const uint32_t t_ahi = t_acc + (uint32_t)m.acc_cols, t_alo = t_ahi + (uint32_t)m.ta_cols;
-              for (int ks = 0; ks < K / 16; ++ks) {
-                const uint64_t bh = make_desc(wh + (uint32_t)ks * kstep_bytes, (uint32_t)N * 16u, 128), bl = make_desc(wl + (uint32_t)ks * kstep_bytes, (uint32_t)N * 16u, 128);
-                umma_bf16_ts(t_acc, t_ahi + (uint32_t)(ks * 8), bh, idesc, ks != 0);
-                umma_bf16_ts(t_acc, t_ahi + (uint32_t)(ks * 8), bl, idesc, 1u);
-                umma_bf16_ts(t_acc, t_alo + (uint32_t)(ks * 8), bh, idesc, 1u);
-              }
+              a_h += (2 * CHUNK >> 4) - 8u; a_l += (2 * CHUNK >> 4) - 8u;
             }
-            umma_commit(bar_acc0 + 8 * g);
+            // relation slab pair (no swizzle: K-slabs 2048 B apart, 8-row groups 128 B apart)
+            const uint32_t r_h = (((smem_s + (uint32_t)g * gbytes + (uint32_t)(m.nchunks * 2 * CHUNK)) >> 4) & 0x3fffu) | ((2048u >> 4) << 16);
+            const uint32_t r_l = r_h + (REL_PLANE >> 4);
+            umma_bf16(t_acc, desc64(r_h, b_hi32), desc64(b_h, b_hi32), idesc, 1u);
+            umma_bf16(t_acc, desc64(r_h, b_hi32), desc64(b_l, b_hi32), idesc, 1u);
+            umma_bf16(t_acc, desc64(r_l, b_hi32), desc64(b_h, b_hi32), idesc, 1u);
+          } else {
+            uint32_t t_ahi = t_acc + (uint32_t)m.acc_cols, t_alo = t_ahi + (uint32_t)m.ta_cols;
+            const int ksteps = lay_ksteps[l];
+            umma_bf16_ts(t_acc, t_ahi, desc64(b_h, b_hi32), idesc, 0u);
+            umma_bf16_ts(t_acc, t_ahi, desc64(b_l, b_hi32), idesc, 1u);
+            umma_bf16_ts(t_acc, t_alo, desc64(b_h, b_hi32), idesc, 1u);
+            for (int ks = 1; ks < ksteps; ++ks) {
+              t_ahi += 8u; t_alo += 8u; b_h += kinc; b_l += kinc;
+              umma_bf16_ts(t_acc, t_ahi, desc64(b_h, b_hi32), idesc, 1u);
+              umma_bf16_ts(t_acc, t_ahi, desc64(b_l, b_hi32), idesc, 1u);
+              umma_bf16_ts(t_acc, t_alo, desc64(b_h, b_hi32), idesc, 1u);
+            }
           }
-          __syncwarp();
+          umma_commit(bar_acc0 + 8 * g);
         }
+        __syncwarp();
+        if (iprof) { const long long t = clock64(); a.prof[49 + (l < 3 ? l : 3)] += t - ti; a.prof[53] += 1; ti = t; }   // time spent issuing layer l
       }
+      if (any) idle = 0;
+      else if (++idle > (1u << 26)) __trap();
     }
   }
   tc_fence_before();
@@ -494,8 +573,16 @@ static int launch_ng(const Args &a, Plan m, long long tiles, cudaStream_t stream
   return launch_status("tc2_fused_mlp");
 }
 
+static long long *g_prof = nullptr;
+
 template <int MODE>
-static int launch(const Args &a, const Plan &m, long long tiles, cudaStream_t stream) {
+static int launch(const Args &a_in, const Plan &m, long long tiles, cudaStream_t stream) {
+  Args a = a_in;
+  static const bool want_prof = getenv("MVPNET_B200_TC2_PROF") != nullptr;
+  if (want_prof) {                 // debug only: phase clocks of CTA 0, printed and reset by mvp_tc2_prof_dump()
+    if (g_prof == nullptr) { cudaMalloc(&g_prof, 64 * sizeof(long long)); cudaMemset(g_prof, 0, 64 * sizeof(long long)); }
+    a.prof = g_prof;
+  }
   int ng = m.groups;
   const long long per_sm = tiles / sm_count();
   if (per_sm < ng) ng = per_sm < 1 ? 1 : (int)per_sm;
@@ -527,6 +614,19 @@ static int to_plan(const mvp_tc_chain_t *c, int mode, int64_t C, Plan *m) {
 
 }  // namespace tc2
 }  // namespace mvp
+
+extern "C" void mvp_tc2_prof_dump(const char *tag) {
+  if (mvp::tc2::g_prof == nullptr) return;
+  long long h[64];
+  cudaDeviceSynchronize();
+  cudaMemcpy(h, mvp::tc2::g_prof, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaMemset(mvp::tc2::g_prof, 0, sizeof(h));
+  fprintf(stderr, "[tc2 prof %s] (cycles of CTA 0, summed over launches)\n", tag);
+  for (int g = 0; g < 3; ++g)
+    fprintf(stderr, "  group %d: wait_gather %lld  wait_L0 %lld  build %lld  epi0 %lld  wait_L1 %lld  epi1 %lld  wait_L2 %lld  epi2 %lld  wait_L3 %lld epi3 %lld\n", g,
+            h[g * 16], h[g * 16 + 1], h[g * 16 + 2], h[g * 16 + 3], h[g * 16 + 4], h[g * 16 + 5], h[g * 16 + 6], h[g * 16 + 7], h[g * 16 + 8], h[g * 16 + 9]);
+  fprintf(stderr, "  issuer: polling %lld  issue_L0 %lld  issue_L1 %lld  issue_L2 %lld  issue_L3+ %lld  requests %lld\n", h[48], h[49], h[50], h[51], h[52], h[53]);
+}
 
 extern "C" int mvp_tc2_supported(const mvp_tc_chain_t *c, int mode, int64_t C) {
   mvp::tc2::Plan m;

@@ -91,6 +91,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!ok && ++spins > (1u << 26)) __trap();
   } while (!ok);
 }
+// Worker-side wait on the accumulator: try_wait suspends the warp in hardware.  The fused kernels are issue-bound (ncu,
+// round 2: a third of all issued warp instructions were test_wait spins of idle tile groups), so a waiting group must
+// not compete for issue slots with the groups that have work.
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1u << 22)) __trap();
+  } while (!ok);
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -461,7 +479,7 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_aready);
-        mbar_wait(bar_acc, acc_phase);
+        mbar_wait_suspend(bar_acc, acc_phase);
         acc_phase ^= 1u;
         tc_fence_after();
         if (!layer_done) continue;                          // next K panel of the first layer: rebuild the activation tile
@@ -568,15 +586,15 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
         int l, kbeg, klen;
         seg_info(sg, l, kbeg, klen);
         const int K = m.k[l], N = m.n[l];
+        if (m.resident) {
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if (r * NG + g >= n_my) continue;
-          mbar_wait(bar_aready0 + 8 * g, ph[g]);
-          ph[g] ^= 1u;
-          tc_fence_after();
-          const uint32_t a_hi_s = smem_s + (uint32_t)((size_t)g * 2 * a_bytes), a_lo_s = a_hi_s + (uint32_t)a_bytes;
-          const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
-          if (m.resident) {
+          for (int g = 0; g < NG; ++g) {
+            if (r * NG + g >= n_my) continue;
+            mbar_wait(bar_aready0 + 8 * g, ph[g]);
+            ph[g] ^= 1u;
+            tc_fence_after();
+            const uint32_t a_hi_s = smem_s + (uint32_t)((size_t)g * 2 * a_bytes), a_lo_s = a_hi_s + (uint32_t)a_bytes;
+            const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
             const uint32_t wbase = wreg_s + (uint32_t)m.res_off[l];
             if (elect_one()) {
               for (int n0 = 0; n0 < N; n0 += 256) {
@@ -592,28 +610,48 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
               umma_commit(bar_acc0 + 8 * g);
             }
             __syncwarp();
-          } else {
-            const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
-            for (int c = 0; c < total; ++c) {
-              const uint32_t s = q_cons % S;
-              const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
-              const uint32_t nb = (uint32_t)min(256, N - n0);
-              const int kc = min(m.kc, kbeg + klen - k0);
-              const uint32_t idesc = make_idesc(ROWS, (int)nb);
-              mbar_wait(bar_full0 + 8 * s, (q_cons / S) & 1u);                       // the chunk has landed
-              const uint32_t wh = wreg_s + s * (uint32_t)(2 * stage_half), wl = wh + (uint32_t)stage_half;
-              if (elect_one()) {
+          }
+        } else {
+          // Streamed weights: every ring stage is used by ALL tile groups of the round before it is released (chunk-major,
+          // group-minor).  Round 1 streamed a layer's weights once per group: the wide chains (FP4: 278 KB per 128 rows)
+          // were bound by that L2 -> shared-memory traffic; sharing a stage divides it by the group count.
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (r * NG + g >= n_my) continue;
+            mbar_wait(bar_aready0 + 8 * g, ph[g]);
+            ph[g] ^= 1u;
+          }
+          tc_fence_after();
+          const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
+          for (int c = 0; c < total; ++c) {
+            const uint32_t s = q_cons % S;
+            const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+            const uint32_t nb = (uint32_t)min(256, N - n0);
+            const int kc = min(m.kc, kbeg + klen - k0);
+            const uint32_t idesc = make_idesc(ROWS, (int)nb);
+            mbar_wait(bar_full0 + 8 * s, (q_cons / S) & 1u);                       // the chunk has landed
+            const uint32_t wh = wreg_s + s * (uint32_t)(2 * stage_half), wl = wh + (uint32_t)stage_half;
+            if (elect_one()) {
+#pragma unroll
+              for (int g = 0; g < NG; ++g) {
+                if (r * NG + g >= n_my) continue;
+                const uint32_t a_hi_s = smem_s + (uint32_t)((size_t)g * 2 * a_bytes), a_lo_s = a_hi_s + (uint32_t)a_bytes;
+                const uint32_t t_group = tmem_base + (uint32_t)(g * m.tmem_cols);
                 for (int j = 0; j < kc; j += 16) {
                   const uint32_t ka = (uint32_t)((k0 + j - kbeg) >> 3), js = (uint32_t)(j >> 3);
                   issue_kstep(t_group + (uint32_t)n0, a_hi_s + ka * SLAB, a_lo_s + ka * SLAB, wh + js * nb * 16, wl + js * nb * 16, nb,
                               idesc, k0 + j == 0);
                 }
-                umma_commit(bar_empty0 + 8 * s);                                     // frees the stage when these MMAs retire
-                if (c == total - 1) umma_commit(bar_acc0 + 8 * g);
               }
-              __syncwarp();
-              ++q_cons;
+              umma_commit(bar_empty0 + 8 * s);                                     // frees the stage when these MMAs retire
+              if (c == total - 1) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                  if (r * NG + g < n_my) umma_commit(bar_acc0 + 8 * g);
+              }
             }
+            __syncwarp();
+            ++q_cons;
           }
         }
       }
@@ -628,24 +666,22 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
         seg_info(sg, l, kbeg, klen);
         const int K = m.k[l], N = m.n[l];
         const int kchunks = (klen + m.kc - 1) / m.kc, nblocks = (N + 255) / 256, total = kchunks * nblocks;
-        for (int g = 0; g < NG; ++g) {
-          if (r * NG + g >= n_my) continue;
-          for (int c = 0; c < total; ++c) {
-            const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
-            const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kbeg + klen - k0);
-            const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
-            if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);  // MMAs of the previous use have retired
-            const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
-            const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
-            const uint32_t dst = wreg_s + s * (uint32_t)(2 * stage_half);
-            if (elect_one()) {
-              mbar_expect_tx(bar_full0 + 8 * s, 2 * bytes);
-              bulk_g2s(dst, gh, bytes, bar_full0 + 8 * s);
-              bulk_g2s(dst + (uint32_t)stage_half, gl, bytes, bar_full0 + 8 * s);
-            }
-            __syncwarp();
-            ++q_prod;
+        if (r * NG >= n_my) continue;
+        for (int c = 0; c < total; ++c) {      // once per round: the stage is shared by the round's tile groups
+          const int n0 = (c / kchunks) * 256, k0 = kbeg + (c % kchunks) * m.kc;
+          const uint32_t nb = (uint32_t)min(256, N - n0), kc = (uint32_t)min(m.kc, kbeg + klen - k0);
+          const uint32_t s = q_prod % S, bytes = (kc >> 3) * nb * 16;
+          if (q_prod >= S) mbar_wait(bar_empty0 + 8 * s, ((q_prod / S) - 1) & 1u);  // MMAs of the previous use have retired
+          const unsigned char *gh = reinterpret_cast<const unsigned char *>(m.w_hi[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+          const unsigned char *gl = reinterpret_cast<const unsigned char *>(m.w_lo[l]) + (size_t)n0 * K * 2 + (size_t)(k0 >> 3) * nb * 16;
+          const uint32_t dst = wreg_s + s * (uint32_t)(2 * stage_half);
+          if (elect_one()) {
+            mbar_expect_tx(bar_full0 + 8 * s, 2 * bytes);
+            bulk_g2s(dst, gh, bytes, bar_full0 + 8 * s);
+            bulk_g2s(dst + (uint32_t)stage_half, gl, bytes, bar_full0 + 8 * s);
           }
+          __syncwarp();
+          ++q_prod;
         }
       }
     }

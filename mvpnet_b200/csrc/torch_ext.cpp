@@ -205,6 +205,93 @@ at::Tensor interpolate_backward(const at::Tensor grad_output, const at::Tensor i
   return grad_input;
 }
 
+#define CHECK_F32(x) TORCH_CHECK((x).scalar_type() == at::kFloat, #x " must be float32")
+// ---- deterministic backward variants (csrc/train_ops.cu): same signatures as the reference's backward functions
+at::Tensor group_points_backward_det(const at::Tensor grad_output, const at::Tensor index, const int64_t num_points) {
+  CHECK_CUDA(grad_output);
+  CHECK_CUDA(index);
+  TORCH_CHECK(grad_output.dim() == 4 && index.dim() == 3, "group_points_backward: grad_output (B,C,N2,K), index (B,N2,K)");
+  TORCH_CHECK(index.size(0) == grad_output.size(0) && index.size(1) == grad_output.size(2) && index.size(2) == grad_output.size(3),
+              "group_points_backward: shape mismatch");
+  TORCH_CHECK(index.scalar_type() == at::kLong, "index must be int64");
+  TORCH_CHECK(grad_output.scalar_type() == at::kFloat, "deterministic backward is float32 only");
+  c10::cuda::CUDAGuard guard(grad_output.device());
+  const auto g = grad_output.contiguous();
+  const auto idx = index.contiguous();
+  const auto B = g.size(0), C = g.size(1), N2 = g.size(2), K = g.size(3);
+  auto grad_input = at::empty({B, C, num_points}, g.options());
+  auto ws = at::empty({mvp_scatter_det_workspace_bytes(B, C, num_points, N2, K, 0)}, g.options().dtype(at::kByte));
+  check_rc(mvp_group_points_backward_det(g.data_ptr<float>(), idx.data_ptr<int64_t>(), B, C, num_points, N2, K, grad_input.data_ptr<float>(),
+                                         ws.data_ptr(), cur_stream()));
+  return grad_input;
+}
+
+at::Tensor interpolate_backward_det(const at::Tensor grad_output, const at::Tensor index, const at::Tensor weight, const int64_t num_inst) {
+  check_interp(grad_output, index, weight, grad_output.size(2));
+  TORCH_CHECK(grad_output.scalar_type() == at::kFloat, "deterministic backward is float32 only");
+  c10::cuda::CUDAGuard guard(grad_output.device());
+  const auto g = grad_output.contiguous();
+  const auto idx = index.contiguous();
+  const auto w = weight.contiguous();
+  const auto B = g.size(0), C = g.size(1), N = g.size(2);
+  auto grad_input = at::empty({B, C, num_inst}, g.options());
+  auto ws = at::empty({mvp_scatter_det_workspace_bytes(B, C, num_inst, N, 3, 1)}, g.options().dtype(at::kByte));
+  check_rc(mvp_interpolate_backward_det(g.data_ptr<float>(), idx.data_ptr<int64_t>(), w.data_ptr<float>(), B, C, num_inst, N,
+                                        grad_input.data_ptr<float>(), ws.data_ptr(), cur_stream()));
+  return grad_input;
+}
+
+// ---- SegLoss / SegAccuracy / SegIoU statistics (csrc/train_ops.cu; mvpnet/models/loss.py, metric.py)
+// returns (loss_out float[2] = {loss, sum of weights}, lse float (B, N), conf int64 (C, C) = confusion matrix of this call)
+std::vector<at::Tensor> seg_loss_forward(const at::Tensor logit, const at::Tensor label, const c10::optional<at::Tensor> weight,
+                                         int64_t ignore_index) {
+  CHECK_INPUT(logit); CHECK_INPUT(label); CHECK_F32(logit);
+  TORCH_CHECK(logit.dim() == 3 && label.dim() == 2 && label.size(0) == logit.size(0) && label.size(1) == logit.size(2),
+              "seg_loss: logit (B, C, N), label (B, N)");
+  TORCH_CHECK(label.scalar_type() == at::kLong, "seg_loss: label must be int64");
+  const float *wp = nullptr;
+  if (weight.has_value() && weight->defined()) {
+    CHECK_INPUT((*weight)); CHECK_F32((*weight));
+    TORCH_CHECK(weight->numel() == logit.size(1), "seg_loss: weight must have one entry per class");
+    wp = weight->data_ptr<float>();
+  }
+  c10::cuda::CUDAGuard guard(logit.device());
+  const auto B = logit.size(0), C = logit.size(1), N = logit.size(2);
+  auto out = at::empty({2}, logit.options());
+  auto lse = at::empty({B, N}, logit.options());
+  auto conf = at::zeros({C, C}, logit.options().dtype(at::kLong));
+  auto ws = at::empty({mvp_seg_loss_workspace_bytes(B, N)}, logit.options().dtype(at::kByte));
+  check_rc(mvp_seg_loss_forward(logit.data_ptr<float>(), label.data_ptr<int64_t>(), wp, B, C, N, ignore_index, lse.data_ptr<float>(),
+                                out.data_ptr<float>(), (uint64_t *)conf.data_ptr<int64_t>(), ws.data_ptr(), cur_stream()));
+  return {out, lse, conf};
+}
+
+at::Tensor seg_loss_backward(const at::Tensor logit, const at::Tensor label, const c10::optional<at::Tensor> weight, const at::Tensor lse,
+                             const at::Tensor loss_out, const at::Tensor grad_scale, int64_t ignore_index) {
+  CHECK_INPUT(logit); CHECK_INPUT(label); CHECK_INPUT(lse); CHECK_INPUT(loss_out); CHECK_INPUT(grad_scale);
+  CHECK_F32(logit); CHECK_F32(lse); CHECK_F32(loss_out); CHECK_F32(grad_scale);
+  const float *wp = nullptr;
+  if (weight.has_value() && weight->defined()) wp = weight->data_ptr<float>();
+  c10::cuda::CUDAGuard guard(logit.device());
+  auto grad = at::empty_like(logit);
+  check_rc(mvp_seg_loss_backward(logit.data_ptr<float>(), label.data_ptr<int64_t>(), wp, lse.data_ptr<float>(), loss_out.data_ptr<float>(),
+                                 grad_scale.data_ptr<float>(), logit.size(0), logit.size(1), logit.size(2), ignore_index,
+                                 grad.data_ptr<float>(), cur_stream()));
+  return grad;
+}
+
+// adds the confusion matrix of (argmax(logit), label) into conf (int64 (C, C)) in place
+void seg_confusion(const at::Tensor logit, const at::Tensor label, int64_t ignore_index, at::Tensor conf) {
+  CHECK_INPUT(logit); CHECK_INPUT(label); CHECK_INPUT(conf); CHECK_F32(logit);
+  TORCH_CHECK(logit.dim() == 3 && label.dim() == 2 && label.size(0) == logit.size(0) && label.size(1) == logit.size(2),
+              "seg_confusion: logit (B, C, N), label (B, N)");
+  TORCH_CHECK(label.scalar_type() == at::kLong && conf.scalar_type() == at::kLong && conf.numel() == logit.size(1) * logit.size(1),
+              "seg_confusion: label int64, conf int64 (C, C)");
+  c10::cuda::CUDAGuard guard(logit.device());
+  check_rc(mvp_seg_confusion(logit.data_ptr<float>(), label.data_ptr<int64_t>(), logit.size(0), logit.size(1), logit.size(2), ignore_index,
+                             (uint64_t *)conf.data_ptr<int64_t>(), cur_stream()));
+}
+
 // ---- data side of FeatureAggregation (no reference extension; scannet_2d3d.py:33-39,255-313) ----
 std::vector<at::Tensor> unproject(const at::Tensor depth, const at::Tensor cam_inv, const at::Tensor pose,
                                   const c10::optional<at::Tensor> chunk_box, bool want_xyz64) {
@@ -290,7 +377,6 @@ struct Chain {
   }
 };
 
-#define CHECK_F32(x) TORCH_CHECK((x).scalar_type() == at::kFloat, #x " must be float32")
 
 at::Tensor fused_set_abstraction(const c10::optional<at::Tensor> feat, const at::Tensor xyz, const at::Tensor new_xyz,
                                  const at::Tensor nbr, const std::vector<at::Tensor> wts, const std::vector<at::Tensor> biases,
@@ -686,21 +772,28 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   auto gp = m.def_submodule("group_points_cuda");
   gp.def("group_points_forward", &group_points_forward, "Group points forward (CUDA)");
   gp.def("group_points_backward", &group_points_backward, "Group points backward (CUDA)");
+  gp.def("group_points_backward_det", &group_points_backward_det, "Group points backward, deterministic summation order (CUDA)");
   auto knn = m.def_submodule("knn_distance_cuda");
   knn.def("knn_distance", &knn_distance, "k-nearest neighbor with distance (CUDA)");
   auto ip = m.def_submodule("interpolate_cuda");
   ip.def("interpolate_forward", &interpolate_forward, "Interpolate feature forward (CUDA)");
   ip.def("interpolate_backward", &interpolate_backward, "Interpolate feature backward (CUDA)");
+  ip.def("interpolate_backward_det", &interpolate_backward_det, "Interpolate feature backward, deterministic summation order (CUDA)");
   auto ds = m.def_submodule("unproject_cuda");
   ds.def("unproject", &unproject, "Depth unprojection (CUDA)");
   ds.def("knn_pixels", &knn_pixels, "2D->3D k-NN over valid pixels (CUDA)", py::arg("query"), py::arg("pix_xyz"),
          py::arg("mask"), py::arg("k"), py::arg("exhaustive") = false);
+  auto tr = m.def_submodule("train_cuda");
+  tr.def("seg_loss_forward", &seg_loss_forward, "weighted cross entropy + confusion matrix, deterministic (CUDA)");
+  tr.def("seg_loss_backward", &seg_loss_backward, "gradient of the weighted cross entropy w.r.t. the logits (CUDA)");
+  tr.def("seg_confusion", &seg_confusion, "confusion matrix of argmax(logit) vs label, accumulated in place (CUDA)");
   auto fz = m.def_submodule("fused_cuda");
   fz.def("set_abstraction", &fused_set_abstraction, "gather + MLP + max (CUDA)");
   fz.def("feature_aggregation", &fused_feature_aggregation, "pixel gather + relation + MLP + sum/max (CUDA)");
   fz.def("feature_propagation", &fused_feature_propagation, "3-NN interpolate + concat + MLP (CUDA)");
   fz.def("tc_chain_supported", &tc_chain_supported, "does the chain fit the tcgen05 kernel");
   fz.def("tc_set_abstraction", &tc_set_abstraction, "gather + MLP (tcgen05) + max");
+  fz.def("tc2_prof_dump", [](const std::string &tag) { mvp_tc2_prof_dump(tag.c_str()); }, "debug: print tc2 phase clocks (MVPNET_B200_TC2_PROF=1)");
   fz.def("tc2_supported", &tc2_supported, "does the chain fit the pre-split-input tcgen05 kernel (csrc/tc2_mlp.cu)");
   fz.def("tc2_set_abstraction", &tc2_set_abstraction, "pre-split gather (cp.async, swizzled operand) + MLP (tcgen05, TMEM activations) + max");
   fz.def("tc2_feature_aggregation", &tc2_feature_aggregation, "pre-split pixel gather + relation + MLP (tcgen05, TMEM activations) + reduce over k");

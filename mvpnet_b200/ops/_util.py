@@ -1,3 +1,5 @@
+import os
+
 import torch
 
 from .. import load_ext
@@ -5,6 +7,14 @@ from .. import load_ext
 
 def ext():
     return load_ext()
+
+
+DETERMINISTIC = os.environ.get('MVPNET_B200_DETERMINISTIC', '1') == '1'
+
+
+def deterministic(grad):
+    """Use the fixed-order backward scatter (float32 only) instead of atomicAdd."""
+    return DETERMINISTIC and grad.dtype == torch.float32
 
 
 def channels_last(x, transpose):

@@ -1,7 +1,9 @@
-"""group_points — mirrors mvpnet/ops/group_points.py:5-31."""
+"""group_points — mirrors mvpnet/ops/group_points.py:5-31.  The backward is the DETERMINISTIC scatter (entries of a
+point added in ascending (n, k) order, csrc/train_ops.cu) for float32; MVPNET_B200_DETERMINISTIC=0 (or float64) selects
+the atomicAdd kernel, whose summation order — like the reference's — changes from run to run."""
 import torch
 
-from ._util import ext
+from ._util import deterministic, ext
 
 
 class GroupPointsFunction(torch.autograd.Function):
@@ -14,7 +16,9 @@ class GroupPointsFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grad_output):
         (index,) = ctx.saved_tensors
-        grad = ext().group_points_cuda.group_points_backward(grad_output[0], index, ctx.num_points)
+        g = grad_output[0]
+        fn = ext().group_points_cuda.group_points_backward_det if deterministic(g) else ext().group_points_cuda.group_points_backward
+        grad = fn(g, index, ctx.num_points)
         return grad, None
 
 

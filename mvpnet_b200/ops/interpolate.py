@@ -1,7 +1,8 @@
-"""feature_interpolate — mirrors mvpnet/ops/interpolate.py:5-34."""
+"""feature_interpolate — mirrors mvpnet/ops/interpolate.py:5-34.  Backward: deterministic scatter for float32 (see
+group_points.py)."""
 import torch
 
-from ._util import ext
+from ._util import deterministic, ext
 
 
 class FeatureInterpolate(torch.autograd.Function):
@@ -14,7 +15,9 @@ class FeatureInterpolate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grad_out):
         index, weight = ctx.saved_tensors
-        grad = ext().interpolate_cuda.interpolate_backward(grad_out[0], index, weight, ctx.n)
+        g = grad_out[0]
+        fn = ext().interpolate_cuda.interpolate_backward_det if deterministic(g) else ext().interpolate_cuda.interpolate_backward
+        grad = fn(g, index, weight, ctx.n)
         return grad, None, None
 
 

@@ -56,7 +56,64 @@ def overlap_matrix(seed=3, num_points=5000, num_frames=40):
     return np.ascontiguousarray(m.T)
 
 
+def boundary_points(seed=21, n=20000):
+    """Extent EXACTLY on a window boundary: x spans 2.5 m, y 3.0 m with chunk 1.5 / stride 0.5, so that
+    (limit - chunk) / stride is an integer in exact arithmetic and the float32 / float64 subtraction of the reference
+    (chunk_util.py:24-28) decides the window count; many points sit exactly on window edges (multiples of 0.5)."""
+    rng = np.random.RandomState(seed)
+    p = rng.rand(n, 3).astype(np.float32) * np.array([2.5, 3.0, 2.0], np.float32) + np.array([0.3, -1.7, 0.0], np.float32)
+    p[:2000, :2] = (np.round(rng.rand(2000, 2) * np.array([5, 6])) * 0.5 + np.array([0.3, -1.7])).astype(np.float32)
+    p[0, :2] = (0.3, -1.7)
+    p[1, :2] = (np.float32(0.3) + np.float32(2.5), np.float32(-1.7) + np.float32(3.0))
+    return p.astype(np.float32)
+
+
+def mvpnet2d_golden():
+    """Reference MVPNet2D (mvpnet/models/mvpnet_2d.py:7-34, imported unmodified) with the reference UNetResNet34 on the
+    seed-0 synthetic chunk and the k-NN indices of rgbd_chunk.npz; group_points served by the oracle."""
+    import types
+    import torch
+    import oracle
+    from mvpnet_b200 import compat
+    compat.install(modules=oracle.ext_modules(), reference_root='/root/reference')
+    for missing in ('open3d', 'natsort'):
+        sys.modules.setdefault(missing, types.ModuleType(missing))
+    from mvpnet.models.mvpnet_2d import MVPNet2D
+    from mvpnet.models.unet_resnet34 import UNetResNet34
+    torch.set_grad_enabled(False)
+    chunk = synthetic.make_chunk(seed=0)
+    knn = np.load(os.path.join(HERE, 'rgbd_chunk.npz'))['knn_indices'].astype(np.int64)
+    model = MVPNet2D(UNetResNet34(20, p=0.5, pretrained=False))
+    synthetic.fill_parameters(model, seed=8).eval()
+    out = model({'images': torch.from_numpy(chunk['images'])[None], 'knn_indices': torch.from_numpy(knn)[None]})['seg_logit']
+    np.savez_compressed(os.path.join(HERE, 'mvpnet2d.npz'), logit_sample=out[0, :, ::4].numpy(), logit_absmax=np.float64(out.abs().max()),
+                        logit_checksum=np.float64(out.double().sum()))
+    print('mvpnet2d', tuple(out.shape), float(out.abs().max()))
+
+
+def nearest_golden():
+    """test_3d_scene.py:155-163: 1-NN label propagation with scikit-learn's ball tree, two votes of 8192 samples."""
+    from sklearn.neighbors import NearestNeighbors
+    pts = scene_points()[:40000]
+    rng = np.random.RandomState(9)
+    ind = np.stack([rng.choice(len(pts), size=8192, replace=False) for _ in range(2)])
+    nn = []
+    for v in range(2):
+        nbrs = NearestNeighbors(n_neighbors=1, algorithm='ball_tree').fit(pts[ind[v]])
+        nn.append(nbrs.kneighbors(pts[:, 0:3])[1][:, 0])
+    np.savez_compressed(os.path.join(HERE, 'nearest_1nn.npz'), vote_indices=ind.astype(np.int32), nn_indices=np.stack(nn).astype(np.int32))
+    print('nearest', np.stack(nn).shape)
+
+
 def main():
+    bp = boundary_points()
+    bidx = chunk_util.scene2chunks_legacy(bp, chunk_size=(1.5, 1.5), stride=0.5, thresh=200, margin=(0.2, 0.2))
+    np.savez_compressed(os.path.join(HERE, 'scene_boundary.npz'), points_checksum=np.float64(bp.astype(np.float64).sum()),
+                        numpy_version=np.__version__, chunk_sizes=np.array([len(i) for i in bidx]),
+                        chunk_index_checksums=np.array([int(i.astype(np.int64).sum()) for i in bidx]))
+    print('boundary chunks', len(bidx), 'numpy', np.__version__)
+    mvpnet2d_golden()
+    nearest_golden()
     pts = scene_points()
     idx, bbox = chunk_util.scene2chunks_legacy(pts, chunk_size=(1.5, 1.5), stride=0.5, thresh=1000, margin=(0.2, 0.2), return_bbox=True)
     # vote accumulation exactly as test_mvpnet_3d.py:136-175, with seeded stand-in logits per chunk

@@ -37,7 +37,32 @@ FULL_GRADS = ('sa_modules.0.mlp.0.conv.weight', 'sa_modules.1.mlp.1.bn.weight', 
 train_inputs = synthetic.train_batch   # seeded inputs of the training step, shared with tests/test_gpu_train.py
 
 
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def run_step(batch, dtype, PN2SSG, SegLoss, SegAccuracy, SegIoU):
+    pts, feat, label, weight = train_inputs(batch)
+    net = synthetic.fill_parameters(PN2SSG(64, NUM_CLASSES, dropout_prob=0.0), seed=5).train().to(dtype)
+    feat = feat.clone().to(dtype).requires_grad_(True)
+    data = {'points': torch.from_numpy(pts.transpose(0, 2, 1).copy()).to(dtype), 'feature': feat, 'seg_label': label}
+    preds = net(data)
+    loss = sum(SegLoss(weight=weight.to(dtype))(preds, data).values())
+    acc, iou = SegAccuracy(), SegIoU(NUM_CLASSES)
+    with torch.no_grad():
+        acc.update_dict(preds, data)
+        iou.update_dict(preds, data)
+    loss.backward()
+    return {'pts': pts, 'feat': feat, 'net': net, 'preds': preds, 'loss': loss, 'acc': acc, 'iou': iou}
+
+
 def main():
+    """Every quantity is stored from a FLOAT64 run of the reference (the truth) together with the deviation of the
+    reference's own FLOAT32 run from it (`noise_*`): train-mode gradients at batch 1 are ill-conditioned (batch statistics
+    over as few as 128 samples, cancellation in the BatchNorm backward) — the reference's fp32 CPU result is itself up to
+    1e-2 of max away from the exact gradient, so the GPU test asks for "as accurate as the reference's fp32", not for
+    agreement with one particular fp32 rounding."""
     compat.install(modules=oracle.ext_modules(), reference_root=REF)
     for missing in ('open3d', 'natsort'):
         sys.modules.setdefault(missing, types.ModuleType(missing))
@@ -46,33 +71,33 @@ def main():
     from mvpnet.models.metric import SegAccuracy, SegIoU
     torch.set_num_threads(os.cpu_count())
     for batch in (1, 32):
-        pts, feat, label, weight = train_inputs(batch)
-        net = synthetic.fill_parameters(PN2SSG(64, NUM_CLASSES, dropout_prob=0.0), seed=5).train()
-        feat = feat.clone().requires_grad_(True)
-        data = {'points': torch.from_numpy(pts.transpose(0, 2, 1).copy()), 'feature': feat, 'seg_label': label}
-        preds = net(data)
-        loss = sum(SegLoss(weight=weight)(preds, data).values())
-        acc, iou = SegAccuracy(), SegIoU(NUM_CLASSES)
-        with torch.no_grad():
-            acc.update_dict(preds, data)
-            iou.update_dict(preds, data)
-        loss.backward()
-        out = {'loss': np.float64(loss.item()), 'acc_tp': np.int64(acc.sum), 'acc_n': np.int64(acc.count),
-               'conf_mat': iou.mat.numpy().astype(np.int64), 'miou': np.float64(iou.global_avg),
-               'logit_sample': preds['seg_logit'].detach()[:, :, ::64].numpy().copy(),
-               'feat_grad_sample': feat.grad[:, :, ::64].numpy().copy(),
-               'in_checksum': np.float64(float(pts.astype(np.float64).sum()) + float(feat.detach().double().sum()))}
-        for name, p in net.named_parameters():
-            out['gn_' + name.replace('.', '_')] = np.float64(p.grad.double().norm().item())
+        r32 = run_step(batch, torch.float32, PN2SSG, SegLoss, SegAccuracy, SegIoU)
+        r64 = run_step(batch, torch.float64, PN2SSG, SegLoss, SegAccuracy, SegIoU)
+        lg32, lg64 = r32['preds']['seg_logit'].detach()[:, :, ::64].numpy(), r64['preds']['seg_logit'].detach()[:, :, ::64].numpy()
+        fg32, fg64 = r32['feat'].grad[:, :, ::64].numpy(), r64['feat'].grad[:, :, ::64].numpy()
+        out = {'loss': np.float64(r64['loss'].item()), 'loss_f32': np.float64(r32['loss'].item()),
+               'acc_tp': np.int64(r32['acc'].sum), 'acc_n': np.int64(r32['acc'].count),
+               'conf_mat': r32['iou'].mat.numpy().astype(np.int64), 'miou': np.float64(r32['iou'].global_avg),
+               'logit_sample': lg64.astype(np.float32), 'noise_logit': np.float64(rel(lg32, lg64)),
+               'feat_grad_sample': fg64.astype(np.float32), 'noise_feat_grad': np.float64(rel(fg32, fg64)),
+               'in_checksum': np.float64(float(r32['pts'].astype(np.float64).sum()) + float(r32['feat'].detach().double().sum()))}
+        p64 = dict(r64['net'].named_parameters())
+        for name, p in r32['net'].named_parameters():
+            key = name.replace('.', '_')
+            g64 = p64[name].grad
+            out['gn_' + key] = np.float64(g64.norm().item())
+            out['noise_' + key] = np.float64(rel(p.grad.numpy(), g64.numpy()))
             if name in FULL_GRADS:
-                out['g_' + name.replace('.', '_')] = p.grad.numpy().copy()
+                out['g_' + key] = g64.numpy().astype(np.float32)
         # running statistics after the step pin the train-mode BatchNorm update (momentum 0.1)
-        sd = net.state_dict()
+        sd = r64['net'].state_dict()
         for name in ('sa_modules.0.mlp.0.bn.running_mean', 'sa_modules.0.mlp.0.bn.running_var', 'fp_modules.3.mlp.2.bn.running_var'):
-            out['rs_' + name.replace('.', '_')] = sd[name].numpy().copy()
+            out['rs_' + name.replace('.', '_')] = sd[name].numpy().astype(np.float32)
         path = os.path.join(HERE, 'pn2_train_b%d.npz' % batch)
         np.savez_compressed(path, **out)
-        print('pn2_train_b%d' % batch, 'loss %.6f' % out['loss'], 'acc %d/%d' % (out['acc_tp'], out['acc_n']), 'miou %.4f' % out['miou'],
+        worst = max((float(v), k) for k, v in out.items() if k.startswith('noise_'))
+        print('pn2_train_b%d' % batch, 'loss %.6f (f32 %.6f)' % (out['loss'], out['loss_f32']), 'acc %d/%d' % (out['acc_tp'], out['acc_n']),
+              'miou %.4f' % out['miou'], 'largest fp32-vs-fp64 deviation of the reference itself: %.2e (%s)' % worst,
               '%.0f KB' % (os.path.getsize(path) / 1024))
 
 

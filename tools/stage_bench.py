@@ -71,3 +71,18 @@ with torch.no_grad():
     print('FA tc2 %.4f ms' % timeit(lambda: ext.fused_cuda.tc2_feature_aggregation(rs, nv, h, w, pix, pts, knn, True, *tc.args(), False, True)))
     print('fps1 %.4f ms' % timeit(lambda: ext.fps_cuda.farthest_point_sample(pts, 2048), 5))
     print('fps2 %.4f ms' % timeit(lambda: ext.fps_cuda.farthest_point_sample(new, 512), 5))
+    # FP4 (+ seg head) and FP3 on the round-1 kernel (weight ring shared by the tile groups)
+    ki, kd = ext.knn_distance_cuda.knn_distance(pts, new, 3)
+    mlp = synthetic.fill_parameters(SharedMLP(128, (128, 128, 128), ndim=1), seed=4).eval().to(dev)
+    seg = synthetic.fill_parameters(SharedMLP(128, (128,), ndim=1), seed=5).eval().to(dev)
+    head = synthetic.fill_parameters(torch.nn.Conv1d(128, 20, 1), seed=6).to(dev)
+    layers = engine._mlp_layers(mlp) + engine._mlp_layers(seg) + [(head, None, False)]
+    tcf = engine.TcChain(layers, 128, dev)
+    sparse = torch.randn(B, 2048, 128, device=dev)
+    print('FP4 tc  %.4f ms' % timeit(lambda: ext.fused_cuda.tc_feature_propagation(sparse, ki, kd, None, 1e-10, *tcf.args())))
+    ki3, kd3 = ext.knn_distance_cuda.knn_distance(new, new2, 3)
+    mlp3 = synthetic.fill_parameters(SharedMLP(320, (256, 128), ndim=1), seed=7).eval().to(dev)
+    tc3 = engine.TcChain(engine._mlp_layers(mlp3), 320, dev)
+    sp3 = torch.randn(B, 512, 256, device=dev)
+    sk3 = torch.randn(B, 2048, 64, device=dev)
+    print('FP3 tc  %.4f ms' % timeit(lambda: ext.fused_cuda.tc_feature_propagation(sp3, ki3, kd3, sk3, 1e-10, *tc3.args())))
