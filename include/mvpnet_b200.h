@@ -117,6 +117,14 @@ int mvp_unproject(const float *depth, const float *cam_inv, const float *pose,
                   const double *chunk_box, int64_t B, int64_t nv, int64_t h, int64_t w,
                   double *xyz64, float *xyz32, uint8_t *mask, mvp_stream_t stream);
 
+/* ---- decoding of the stored input formats on the device (what the dataset holds is what crosses PCIe) ----------
+ * replaces the host-side conversions of mvpnet/data/scannet_2d3d.py:229-251: colour uint8 HWC [N,H,W,3] -> float32
+ * CHW [N,3,H,W] as (u8 / 255 - mean[c]) / std[c] (float32, in that order; mean3 / std3 are HOST arrays of 3 floats);
+ * depth uint16 millimetres -> float32 metres as float32(mm) / 1000. */
+int mvp_decode_rgb_u8(const uint8_t *rgb_hwc, int64_t N, int64_t H, int64_t W, const float *mean3, const float *std3,
+                      float *out_chw, mvp_stream_t stream);
+int mvp_decode_depth_u16(const uint16_t *depth_mm, int64_t count, float *depth_m, mvp_stream_t stream);
+
 /* ---- 2D->3D k-NN over valid pixels -------------------------------------------------------------
  * replaces sklearn NearestNeighbors(k,'ball_tree').fit(valid).kneighbors(points) + the remap to
  * flat pixel ids, mvpnet/data/scannet_2d3d.py:298-313.  query [B,nq,3] f64 (chunk points),

@@ -206,6 +206,31 @@ at::Tensor interpolate_backward(const at::Tensor grad_output, const at::Tensor i
 }
 
 #define CHECK_F32(x) TORCH_CHECK((x).scalar_type() == at::kFloat, #x " must be float32")
+// ---- stored input formats -> network inputs on the device (csrc/unproject.cu)
+at::Tensor decode_rgb_u8(const at::Tensor rgb, const std::vector<double> mean, const std::vector<double> stddev) {
+  CHECK_INPUT(rgb);
+  TORCH_CHECK(rgb.scalar_type() == at::kByte && rgb.dim() >= 3 && rgb.size(-1) == 3, "decode_rgb_u8: uint8 (..., H, W, 3)");
+  TORCH_CHECK(mean.size() == 3 && stddev.size() == 3, "decode_rgb_u8: three means and three standard deviations");
+  const float m[3] = {(float)mean[0], (float)mean[1], (float)mean[2]}, sd[3] = {(float)stddev[0], (float)stddev[1], (float)stddev[2]};
+  const auto H = rgb.size(-3), W = rgb.size(-2), N = rgb.numel() / (3 * H * W);
+  c10::cuda::CUDAGuard guard(rgb.device());
+  auto sizes = rgb.sizes().vec();
+  sizes[sizes.size() - 3] = 3; sizes[sizes.size() - 2] = H; sizes[sizes.size() - 1] = W;
+  auto out = at::empty(sizes, rgb.options().dtype(at::kFloat));
+  check_rc(mvp_decode_rgb_u8(rgb.data_ptr<uint8_t>(), N, H, W, m, sd, out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
+// depth_mm: int16 tensor holding the uint16 bit patterns of the depth PNGs (torch has no first-class uint16)
+at::Tensor decode_depth_u16(const at::Tensor depth_mm) {
+  CHECK_INPUT(depth_mm);
+  TORCH_CHECK(depth_mm.scalar_type() == at::kShort || depth_mm.scalar_type() == at::kUInt16, "decode_depth_u16: int16 / uint16 bit patterns");
+  c10::cuda::CUDAGuard guard(depth_mm.device());
+  auto out = at::empty(depth_mm.sizes(), depth_mm.options().dtype(at::kFloat));
+  check_rc(mvp_decode_depth_u16((const uint16_t *)depth_mm.data_ptr(), depth_mm.numel(), out.data_ptr<float>(), cur_stream()));
+  return out;
+}
+
 // ---- deterministic backward variants (csrc/train_ops.cu): same signatures as the reference's backward functions
 at::Tensor group_points_backward_det(const at::Tensor grad_output, const at::Tensor index, const int64_t num_points) {
   CHECK_CUDA(grad_output);
@@ -781,6 +806,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   ip.def("interpolate_backward_det", &interpolate_backward_det, "Interpolate feature backward, deterministic summation order (CUDA)");
   auto ds = m.def_submodule("unproject_cuda");
   ds.def("unproject", &unproject, "Depth unprojection (CUDA)");
+  ds.def("decode_rgb_u8", &decode_rgb_u8, "uint8 HWC colour -> normalised float32 CHW (CUDA)");
+  ds.def("decode_depth_u16", &decode_depth_u16, "uint16 millimetre depth -> float32 metres (CUDA)");
   ds.def("knn_pixels", &knn_pixels, "2D->3D k-NN over valid pixels (CUDA)", py::arg("query"), py::arg("pix_xyz"),
          py::arg("mask"), py::arg("k"), py::arg("exhaustive") = false);
   auto tr = m.def_submodule("train_cuda");

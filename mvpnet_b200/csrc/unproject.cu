@@ -54,7 +54,53 @@ unproject_kernel(const float *__restrict__ depth, const float *__restrict__ cam_
   if (mask) mask[g] = ok ? 1 : 0;
 }
 
+// ---- decoding of the STORED input formats on the device (the host uploads what the dataset stores, 4x / 2x fewer bytes):
+//   colour  uint8 HWC (PIL, scannet_2d3d.py:229-246) -> float32 CHW: (u8 / 255 - mean[c]) / std[c], each step rounded to
+//           float32 in that order (np.float32 image / 255., then the normaliser's subtract and divide);
+//   depth   uint16 millimetres (scannet_2d3d.py:249-251) -> float32 metres: float32(mm) / 1000.
+__global__ void __launch_bounds__(256)
+decode_rgb_kernel(const uint8_t *__restrict__ rgb /*[N][H][W][3]*/, long long total /*N*H*W*/, int hw, float m0, float m1, float m2, float s0,
+                  float s1, float s2, float *__restrict__ out /*[N][3][H][W]*/) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long n = i / hw;
+    const int p = (int)(i - n * hw);
+    const uint8_t *s = rgb + i * 3;
+    float *o = out + n * 3 * hw + p;
+    o[0] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[0], 255.f), m0), s0);
+    o[hw] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[1], 255.f), m1), s1);
+    o[2 * (size_t)hw] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[2], 255.f), m2), s2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+decode_depth_kernel(const uint16_t *__restrict__ mm, long long total, float *__restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) out[i] = __fdiv_rn((float)mm[i], 1000.f);
+}
+
 }  // namespace mvp
+
+extern "C" int mvp_decode_rgb_u8(const uint8_t *rgb_hwc, int64_t N, int64_t H, int64_t W, const float *mean3, const float *std3,
+                                 float *out_chw, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(N >= 0 && H >= 0 && W >= 0 && H * W < (1LL << 31), MVP_ERR_INVALID_ARG, "decode_rgb_u8: bad sizes");
+  if (N * H * W == 0) return 0;
+  MVP_REQUIRE(rgb_hwc && mean3 && std3 && out_chw, MVP_ERR_NULL, "decode_rgb_u8: null pointer (mean3 / std3 are HOST arrays of 3 floats)");
+  const long long total = N * H * W;
+  const long long want = (total + 255) / 256, cap = (long long)sm_count() * 16;
+  decode_rgb_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(rgb_hwc, total, (int)(H * W), mean3[0], mean3[1], mean3[2], std3[0],
+                                                                                           std3[1], std3[2], out_chw);
+  return launch_status("decode_rgb_u8");
+}
+
+extern "C" int mvp_decode_depth_u16(const uint16_t *depth_mm, int64_t count, float *depth_m, mvp_stream_t stream) {
+  using namespace mvp;
+  MVP_REQUIRE(count >= 0, MVP_ERR_INVALID_ARG, "decode_depth_u16: bad size");
+  if (count == 0) return 0;
+  MVP_REQUIRE(depth_mm && depth_m, MVP_ERR_NULL, "decode_depth_u16: null pointer");
+  const long long want = (count + 255) / 256, cap = (long long)sm_count() * 16;
+  decode_depth_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(depth_mm, count, depth_m);
+  return launch_status("decode_depth_u16");
+}
 
 extern "C" int mvp_unproject(const float *depth, const float *cam_inv, const float *pose, const double *chunk_box,
                              int64_t B, int64_t nv, int64_t h, int64_t w, double *xyz64, float *xyz32, uint8_t *mask,

@@ -79,6 +79,20 @@ def test_fps_tie_order_vs_oracle(ext, n, q):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize('b,n,m,q', [(2, 20000, 1500, 8), (1, 70000, 600, 0), (3, 9001, 1000, 20), (1, 140000, 300, 4)])
+def test_fps_large_clouds_vs_oracle(ext, b, n, m, q):
+    """Whole-scene sizes (N > 8192: the slab kernel with the sorted cloud in a global workspace), random and lattice
+    clouds with exact ties, one and several slabs' worth of points per lane."""
+    rng = np.random.RandomState(n + q)
+    pts = (rng.rand(b, n, 3) * np.array([6.0, 8.0, 2.7])).astype(np.float32)
+    if q:
+        pts = (np.round(pts * q) / q).astype(np.float32)
+        pts[:, n // 2:n // 2 * 2] = pts[:, :n // 2]
+    want = oracle.farthest_point_sample(pts, m)
+    got = ext.fps_cuda.farthest_point_sample(cu(pts), m).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
 def test_fps_errors(ext):
     with pytest.raises(RuntimeError):
         ext.fps_cuda.farthest_point_sample(torch.zeros(1, 8, 4).cuda(), 2)

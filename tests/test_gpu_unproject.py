@@ -104,3 +104,18 @@ def test_knn_pixels_too_few_valid():
     for exhaustive in (False, True):
         gi, _ = ext.unproject_cuda.knn_pixels(torch.ones(1, 2, 3, dtype=torch.float64).cuda(), pix, mask, 3, exhaustive)
         assert gi.cpu().numpy().tolist() == [[[4, -1, -1], [4, -1, -1]]]
+
+
+def test_decode_stored_inputs_bit_exact():
+    """uint8 HWC colour / uint16 mm depth -> network inputs on the device == the host conversions of
+    scannet_2d3d.py:229-251 (float32, same operation order)."""
+    import mvpnet_b200
+    from mvpnet_b200 import engine
+    rng = np.random.RandomState(0)
+    rgb = rng.randint(0, 256, (2, 3, 24, 40, 3)).astype(np.uint8)
+    mm = rng.randint(0, 65536, (2, 3, 24, 40)).astype(np.uint16)
+    out = engine.decode_stored_inputs({'images_u8': torch.from_numpy(rgb).cuda(), 'depth_mm': torch.from_numpy(mm.view(np.int16)).cuda()})
+    want = (rgb.astype(np.float32) / np.float32(255.0) - np.asarray(engine.IMAGE_MEAN, np.float32)) / np.asarray(engine.IMAGE_STD, np.float32)
+    assert out['images'].shape == (2, 3, 3, 24, 40)
+    assert np.array_equal(out['images'].cpu().numpy(), want.transpose(0, 1, 4, 2, 3))
+    assert np.array_equal(out['depth'].cpu().numpy(), mm.astype(np.float32) / np.float32(1000.0))

@@ -28,11 +28,12 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
-    print('| # | kernel | ' + ' | '.join(c[1] for c in COLS) + ' |')
-    print('|---|---|' + '---|' * len(COLS))
+    print('| # | kernel | ' + ' | '.join(c[1] for c in COLS) + ' | dram_GB/s |')
+    print('|---|---|' + '---|' * (len(COLS) + 1))
     tot_ms = tot_mb = 0.0
     for n, r in enumerate(body):
         cells = []
+        row_ms = row_mb = 0.0
         for name, label, scale in COLS:
             if name not in idx:
                 cells.append('')
@@ -41,15 +42,18 @@ def main():
             if scale is None:
                 x = to_mb(v, u)
                 tot_mb += x
+                row_mb += x
                 cells.append('%.2f' % x)
             elif label == 'ms':
                 x = float(v.replace(',', '')) * {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 'nsecond': 1e-6, 'usecond': 1e-3, 'msecond': 1.0}.get(u, 1e-6)
                 tot_ms += x
+                row_ms = x
                 cells.append('%.4f' % x)
             elif label in ('grid', 'block', 'regs'):
                 cells.append(v.replace(',', '').split('.')[0])
             else:
                 cells.append('%.1f' % float(v.replace(',', '')))
+        cells.append('%.0f' % (row_mb / row_ms) if row_ms > 0 else '')      # MB / ms = GB/s achieved DRAM traffic
         print('| %d | %s | ' % (n, r[idx['Kernel Name']][:48]) + ' | '.join(cells) + ' |')
     print()
     print('%d launches, %.3f ms, DRAM read+write %.1f MB (%.1f MB per launch)' % (len(body), tot_ms, tot_mb, tot_mb / max(len(body), 1)))
