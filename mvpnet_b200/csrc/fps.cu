@@ -578,24 +578,43 @@ fps_big_kernel(const float *__restrict__ points, int64_t *__restrict__ index, fl
       }
       unsigned mask = __ballot_sync(0xffffffffu, act);
       while (mask) {
-        const int l = __ffs(mask) - 1;
+        // two active slabs per trip: their (L2-latency) loads are in flight together; a lone slab is paired with itself and
+        // the duplicate's results are dropped
+        const int la = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int sa = (k * 32 + l) * 32 + warp, slot_a = (k * 32 + warp) * 32 + l;
-        float best = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
-        unsigned brk = 0xffffffffu;
+        const bool two = mask != 0u;
+        const int lb = two ? __ffs(mask) - 1 : la;
+        mask &= mask - 1;
+        const int sa = (k * 32 + la) * 32 + warp, slot_a = (k * 32 + warp) * 32 + la;
+        const int sb = (k * 32 + lb) * 32 + warp, slot_b = (k * 32 + warp) * 32 + lb;
+        float best_a = 0.f, ax_ = 0.f, ay_ = 0.f, az_ = 0.f, best_b = 0.f, bx_ = 0.f, by_ = 0.f, bz_ = 0.f;
+        unsigned rk_a = 0xffffffffu, rk_b = 0xffffffffu;
         for (int pp = 0; pp < PPL; ++pp) {
-          const long long base = (long long)sa * SL + pp * 32 + lane;
-          const float x = gx[base], y = gy[base], z = gz[base];
-          const float md = fminf(gmd[base], sqdist3(x, y, z, cx, cy, cz));
-          gmd[base] = md;
-          const unsigned rk = grk[base];
-          if (md > best || (md == best && rk < brk)) { best = md; brk = rk; bx = x; by = y; bz = z; }
+          const long long ba = (long long)sa * SL + pp * 32 + lane, bb = (long long)sb * SL + pp * 32 + lane;
+          const float xa = gx[ba], ya = gy[ba], za = gz[ba], ma = gmd[ba];
+          const unsigned ra = grk[ba];
+          const float xb = gx[bb], yb = gy[bb], zb = gz[bb], mb_ = gmd[bb];
+          const unsigned rb = grk[bb];
+          const float mda = fminf(ma, sqdist3(xa, ya, za, cx, cy, cz)), mdb = fminf(mb_, sqdist3(xb, yb, zb, cx, cy, cz));
+          gmd[ba] = mda;
+          if (two) gmd[bb] = mdb;
+          if (mda > best_a || (mda == best_a && ra < rk_a)) { best_a = mda; rk_a = ra; ax_ = xa; ay_ = ya; az_ = za; }
+          if (mdb > best_b || (mdb == best_b && rb < rk_b)) { best_b = mdb; rk_b = rb; bx_ = xb; by_ = yb; bz_ = zb; }
         }
-        const unsigned mb = __float_as_uint(best);
-        const unsigned m = __reduce_max_sync(0xffffffffu, mb);
-        const unsigned r = __reduce_min_sync(0xffffffffu, mb == m ? brk : 0xffffffffu);
-        const unsigned wb = __ballot_sync(0xffffffffu, mb == m && brk == r);      // every lane votes (never under a condition)
-        if (lane == __ffs(wb) - 1) { m_max[slot_a] = best; m_rank[slot_a] = r; m_wx[slot_a] = bx; m_wy[slot_a] = by; m_wz[slot_a] = bz; }
+        {
+          const unsigned mb = __float_as_uint(best_a);
+          const unsigned m = __reduce_max_sync(0xffffffffu, mb);
+          const unsigned r = __reduce_min_sync(0xffffffffu, mb == m ? rk_a : 0xffffffffu);
+          const unsigned wb = __ballot_sync(0xffffffffu, mb == m && rk_a == r);      // every lane votes (never under a condition)
+          if (lane == __ffs(wb) - 1) { m_max[slot_a] = best_a; m_rank[slot_a] = r; m_wx[slot_a] = ax_; m_wy[slot_a] = ay_; m_wz[slot_a] = az_; }
+        }
+        if (two) {                                                                  // warp-uniform
+          const unsigned mb = __float_as_uint(best_b);
+          const unsigned m = __reduce_max_sync(0xffffffffu, mb);
+          const unsigned r = __reduce_min_sync(0xffffffffu, mb == m ? rk_b : 0xffffffffu);
+          const unsigned wb = __ballot_sync(0xffffffffu, mb == m && rk_b == r);
+          if (lane == __ffs(wb) - 1) { m_max[slot_b] = best_b; m_rank[slot_b] = r; m_wx[slot_b] = bx_; m_wy[slot_b] = by_; m_wz[slot_b] = bz_; }
+        }
       }
     }
     __syncwarp();

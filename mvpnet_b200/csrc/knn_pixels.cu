@@ -261,8 +261,9 @@ kp_scatter_kernel(const double *__restrict__ pix, const uint8_t *__restrict__ ma
   sorted[(size_t)b * P + pos] = r;
 }
 
+// 4 CTAs per SM: 64 registers without spills (98 registers unbounded = 2 CTAs; the kernel is latency-bound, ncu round 1: 30 % warps active)
 template <int KMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ grids, const int *__restrict__ cells,
                 const KpRec *__restrict__ sorted, int nq, int P, int k,
                 int blocks_per_cloud, int64_t *__restrict__ index, double *__restrict__ dist2) {
@@ -282,6 +283,28 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
   int bi[KMAX];
 #pragma unroll
   for (int j = 0; j < KMAX; ++j) { bd[j] = Inf<double>::v(); bi[j] = 0x7fffffff; }
+
+  // a contiguous run of the sorted pixel array, lanes in parallel.  The kernel is bound by the latency of these loads
+  // (profile: 55 % of the stall samples on them, L2 at 11 %): every trip fetches the records of TWO sub-iterations
+  // (two 16-byte loads each) before it evaluates either: 2.13 -> 1.79 ms with KP_SCAN_UNROLL = 2 sub-iterations in flight (4: 2.15 ms — 80 registers, spills, one CTA fewer per SM).
+  auto scan = [&](int beg, int end) {
+    constexpr int U = KP_SCAN_UNROLL;
+    for (int p0 = beg; p0 < end; p0 += 32 * U) {
+      double2 r0[U], r1[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int p = p0 + 32 * u + lane;
+        ok[u] = p < end;
+        r0[u] = make_double2(0.0, 0.0);
+        r1[u] = r0[u];
+        if (ok[u]) { const double2 *r = reinterpret_cast<const double2 *>(srec + p); r0[u] = __ldg(r); r1[u] = __ldg(r + 1); }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) topk_insert<KMAX>(sqdist3_nofma(r0[u].x, r0[u].y, r1[u].x, qx, qy, qz), (int)__double_as_longlong(r1[u].y), bd, bi);
+    }
+  };
 
   double kth = Inf<double>::v();   // k-th best squared distance over the whole warp so far
   for (int r = 0; r <= rmax; ++r) {
@@ -308,45 +331,12 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
           }
         }
       }
-      // Stream the CONCATENATION of the (up to 64) runs of these positions with every lane busy and KP_SCAN_UNROLL record
-      // loads in flight per lane (round 1 scanned run after run: a shell of short runs cost one dependent load round per
-      // run with most lanes idle — the record loads were 55 % of this kernel's stall samples).
-      const int len0 = max(end0 - beg0, 0), len1 = max(end1 - beg1, 0);
-      int total = 0;
-      int inc = len0 + len1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int tt = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += tt;
-      }
-      total = __shfl_sync(0xffffffffu, inc, 31);
-      const int excl = inc - (len0 + len1);
-      constexpr int U = KP_SCAN_UNROLL;
-      for (int k0 = 0; k0 < total; k0 += 32 * U) {
-        double2 r0[U], r1[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int kk = k0 + 32 * u + lane;
-          ok[u] = kk < total;
-          const int kq = min(kk, total - 1);
-          int o = 0;                                            // owner lane: the last one whose prefix is <= kq
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1) {
-            const int cand = o + step;
-            const int e = __shfl_sync(0xffffffffu, excl, cand);
-            if (e <= kq) o = cand;
-          }
-          const int off = kq - __shfl_sync(0xffffffffu, excl, o);
-          const int b0 = __shfl_sync(0xffffffffu, beg0, o), l0 = __shfl_sync(0xffffffffu, len0, o), b1 = __shfl_sync(0xffffffffu, beg1, o);
-          const int p = off < l0 ? b0 + off : b1 + (off - l0);
-          r0[u] = make_double2(0.0, 0.0);
-          r1[u] = r0[u];
-          if (ok[u]) { const double2 *rr = reinterpret_cast<const double2 *>(srec + p); r0[u] = __ldg(rr); r1[u] = __ldg(rr + 1); }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (ok[u]) topk_insert<KMAX>(sqdist3_nofma(r0[u].x, r0[u].y, r1[u].x, qx, qy, qz), (int)__double_as_longlong(r1[u].y), bd, bi);
+      unsigned active = __ballot_sync(0xffffffffu, end0 > beg0 || end1 > beg1);
+      while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        scan(__shfl_sync(0xffffffffu, beg0, src), __shfl_sync(0xffffffffu, end0, src));
+        scan(__shfl_sync(0xffffffffu, beg1, src), __shfl_sync(0xffffffffu, end1, src));
       }
     }
     // k-th smallest over the 32 sorted lists (non-destructive merge)

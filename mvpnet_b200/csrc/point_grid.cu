@@ -201,36 +201,6 @@ pg_scatter_kernel(const T *__restrict__ key, int N, const PgGrid<T> *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Streaming several short runs of the sorted array with every lane busy.  Each lane holds up to two runs (beg0, len0),
-// (beg1, len1) of one (y, z) position; `excl` is the exclusive warp prefix sum of len0 + len1 and `total` its sum.
-// pg_locate() maps position k of the CONCATENATED runs to an index of the sorted array: the owner is the last lane whose
-// prefix is <= k (binary search over the lanes by shuffles).  Round 1 scanned run after run — a shell of nine 5-key runs
-// cost nine dependent load rounds with 5 of 32 lanes active; concatenated it is two rounds.  All lanes must call it.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int pg_warp_excl_scan(int v, int lane, int &total) {
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  total = __shfl_sync(0xffffffffu, inc, 31);
-  return inc - v;
-}
-__device__ __forceinline__ int pg_locate(int k, int excl, int beg0, int len0, int beg1) {
-  int o = 0;
-#pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const int cand = o + step;                                  // <= 31
-    const int e = __shfl_sync(0xffffffffu, excl, cand);
-    if (e <= k) o = cand;
-  }
-  const int off = k - __shfl_sync(0xffffffffu, excl, o);
-  const int b0 = __shfl_sync(0xffffffffu, beg0, o), l0 = __shfl_sync(0xffffffffu, len0, o), b1 = __shfl_sync(0xffffffffu, beg1, o);
-  return off < l0 ? b0 + off : b1 + (off - l0);
-}
-
-// ------------------------------------------------------------------------------------------------
 // ball query
 // ------------------------------------------------------------------------------------------------
 // Shared memory per warp: hits[cap] (+ dist[cap]) and the finished row[K] (+ drow[K]); cap = K + 64.
@@ -407,6 +377,13 @@ pg_knn3_kernel(const T *__restrict__ query, const PgGrid<T> *__restrict__ grids,
 
   T bd[3] = {Inf<T>::v(), Inf<T>::v(), Inf<T>::v()};
   int bi[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
+  auto scan = [&](int beg, int end) {  // a contiguous run of the sorted key array, lanes in parallel
+    for (int p = beg + lane; p < end; p += 32) {
+      const PgRec<T> k = pg_load<T>(sp + p);
+      pg_top3_insert(sqdist3(k.x, k.y, k.z, qx, qy, qz), (int)k.i, bd, bi);
+    }
+  };
+
   for (int r = 0; r <= rmax; ++r) {
     // shell r: the (y, z) positions of a (2r+1)^2 square; a rim position contributes its whole x extent (one run),
     // an interior position its two end cells.  Lanes fetch the run boundaries of 32 positions at once.
@@ -429,18 +406,12 @@ pg_knn3_kernel(const T *__restrict__ query, const PgGrid<T> *__restrict__ grids,
           }
         }
       }
-      // stream the concatenation of the (up to 64) runs, two keys per lane in flight
-      const int len0 = max(end0 - beg0, 0), len1 = max(end1 - beg1, 0);
-      int total;
-      const int excl = pg_warp_excl_scan(len0 + len1, lane, total);
-      for (int k0 = 0; k0 < total; k0 += 64) {
-        const int ka = k0 + lane, kb = k0 + 32 + lane;
-        const int pa = pg_locate(min(ka, total - 1), excl, beg0, len0, beg1), pb = pg_locate(min(kb, total - 1), excl, beg0, len0, beg1);
-        PgRec<T> ra, rb;
-        if (ka < total) ra = pg_load<T>(sp + pa);
-        if (kb < total) rb = pg_load<T>(sp + pb);
-        if (ka < total) pg_top3_insert(sqdist3(ra.x, ra.y, ra.z, qx, qy, qz), (int)ra.i, bd, bi);
-        if (kb < total) pg_top3_insert(sqdist3(rb.x, rb.y, rb.z, qx, qy, qz), (int)rb.i, bd, bi);
+      unsigned active = __ballot_sync(0xffffffffu, end0 > beg0 || end1 > beg1);
+      while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        scan(__shfl_sync(0xffffffffu, beg0, src), __shfl_sync(0xffffffffu, end0, src));
+        scan(__shfl_sync(0xffffffffu, beg1, src), __shfl_sync(0xffffffffu, end1, src));
       }
     }
     if (r == rmax) break;

@@ -30,8 +30,7 @@ namespace mvp {
 namespace tc2 {
 using namespace tc;   // PTX wrappers of tc_mlp.cu (same translation unit)
 
-constexpr int GT = 256;             // worker threads per tile group (8 warps)
-constexpr int MAXG = 3;
+constexpr int MAXG = 6;             // tile groups per CTA: 3 of 256 threads (two warps per TMEM lane quarter) or up to 6 of 128 threads
 constexpr int MAXL = 6;
 constexpr int CHUNK = 16384;        // bytes of one plane of a 64-channel chunk of the gathered tile: 128 rows x 128 B
 constexpr int REL_PLANE = 4096;     // bytes of one plane of the relation slab pair: 2 K-slabs x 128 rows x 16 B
@@ -49,7 +48,7 @@ struct Args {
   unsigned hw, w, hp_wp, wp, nv;            // FA: pixel j = (v, y, x) of an nv x h x w stack -> feature row (b*nv+v)*hp_wp + y*wp + x
   float *out_f32;                           // [rows_out, out_channels] or null
   __nv_bfloat16 *out_hi, *out_lo;           // [rows_out, out_channels] or null
-  long long *prof;                          // debug (MVPNET_B200_TC2_PROF): per-phase clock64 sums of CTA 0, or null
+  long long *prof;                          // debug (MVPNET_B200_TC2_PROF): per-phase clock64 sums of CTA 0 (16 words per group, issuer at 96), or null
 };
 
 struct Plan {
@@ -118,6 +117,7 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+template <int GT>
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(GT) : "memory"); }
 
 // the group's unit sequence: tiles blockIdx.x + (g + j * NG) * gridDim.x, each `passes` times (FA: one per pixel slot)
@@ -163,7 +163,11 @@ __device__ __forceinline__ RowRef resolve(const Args &a, const Cursor &c, int r,
   return o;
 }
 
-template <int MODE, int NG>
+// GT = worker threads per tile group: 256 (8 warps, two per TMEM lane quarter taking alternate 16-column chunks) or 128
+// (4 warps, one per quarter).  More, narrower groups keep more units in flight per SM: the phase clocks of the 3 x 256
+// configuration showed a group waiting 40 % of its time on the request -> MMA -> commit round trips with the SM's issue
+// slots half idle.
+template <int MODE, int NG, int GT>
 __global__ void __launch_bounds__(NG *GT + 32, 1)
 tc2_kernel(const Args a, const Plan m, long long num_tiles) {
   extern __shared__ unsigned char smem_raw[];
@@ -214,6 +218,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
     unsigned char *rel_hi = smem + (size_t)g * gbytes + (size_t)m.nchunks * 2 * CHUNK, *rel_lo = rel_hi + REL_PLANE;
     int *src = src_s + g * 128;
     const uint32_t bar_aready = bar_aready0 + 8 * g, bar_acc = bar_acc0 + 8 * g;
+    constexpr int NHALF = GT / 128;                       // warps per TMEM lane quarter
     const int quarter = lwarp & 3, half = lwarp >> 2;
     const uint32_t t_lane = tmem_base + (uint32_t)(g * m.tg_cols) + ((uint32_t)(quarter * 32) << 16);
     const uint32_t t_ahi = t_lane + (uint32_t)m.acc_cols, t_alo = t_ahi + (uint32_t)m.ta_cols, t_part = t_alo + (uint32_t)m.ta_cols;
@@ -256,11 +261,12 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
         *reinterpret_cast<uint4 *>(rel_lo + off) = make_uint4(l0, l1, 0u, 0u);
         src[ltid] = rr.frow;
       }
-      group_bar(g);
+      group_bar<GT>(g);
       const int chunk = lane & 7, rsub = lane >> 3;
+      constexpr int RPP = GT / 8;                          // rows per pass: every warp takes 4
 #pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const int r = ps * 32 + lwarp * 4 + rsub;
+      for (int ps = 0; ps < 128 / RPP; ++ps) {
+        const int r = ps * RPP + lwarp * 4 + rsub;
         const int s = src[r];
         const uint32_t nbytes = s >= 0 ? 16u : 0u;
         const size_t e = (size_t)(s >= 0 ? s : 0) * a.C + chunk * 8;
@@ -326,7 +332,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
           tmem_ld_wait(rn);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
-          if ((c + 2) * 16 < N) tmem_ld16_issue(t_lane + (uint32_t)((c + 2) * 16), rn);
+          if ((c + NHALF) * 16 < N) tmem_ld16_issue(t_lane + (uint32_t)((c + NHALF) * 16), rn);
           const float4 *bp = reinterpret_cast<const float4 *>(bs + c * 16);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -404,7 +410,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
               }
             }
           }
-          c += 2;
+          c += NHALF;
         }
         if (last && MODE == MODE_FA) tmem_st_wait();   // the partial columns are re-read by this thread in the next slot
         mark(3 + 2 * l);
@@ -425,9 +431,9 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
     // The whole warp polls the groups' request barriers and serves WHICHEVER group is ready (a fixed round-robin order
     // made the groups advance in lock step: all of them in their epilogues while the tensor pipe idled, then all of
     // them waiting); every value is warp-uniform, one elected lane issues.
-    uint32_t ph[MAXG] = {0u, 0u, 0u};
-    int layer[MAXG] = {0, 0, 0};
-    long long left[MAXG] = {0, 0, 0};
+    uint32_t ph[MAXG] = {};
+    int layer[MAXG] = {};
+    long long left[MAXG] = {};
     long long remaining = 0;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -435,18 +441,6 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
       remaining += left[g];
     }
     const uint32_t smem_s = smem_u32(smem), wreg_s = smem_u32(wreg);
-    uint32_t lay_idesc[MAXL], lay_bh[MAXL], lay_bl[MAXL], lay_kinc[MAXL];
-    int lay_ksteps[MAXL];
-#pragma unroll
-    for (int l = 0; l < MAXL; ++l) {
-      const int K = l < L ? m.k[l] : 16, N = l < L ? m.n[l] : 16;
-      const uint32_t wh = wreg_s + (uint32_t)(l < L ? m.woff[l] : 0), wl = wh + (uint32_t)(K * N * 2);
-      lay_idesc[l] = make_idesc(128, N);
-      lay_bh[l] = ((wh >> 4) & 0x3fffu) | ((uint32_t)N << 16);        // K-direction stride N * 16 bytes (>> 4)
-      lay_bl[l] = ((wl >> 4) & 0x3fffu) | ((uint32_t)N << 16);
-      lay_kinc[l] = (uint32_t)N * 2u;                                  // 16 channels of the weight operand = N * 32 bytes (>> 4)
-      lay_ksteps[l] = K / 16;
-    }
     uint32_t idle = 0;
     const bool iprof = a.prof != nullptr && blockIdx.x == 0 && lane == 0;
     long long ti = iprof ? clock64() : 0;
@@ -456,7 +450,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
       for (int g = 0; g < NG; ++g) {
         if (left[g] == 0 || !mbar_test(bar_aready0 + 8 * g, ph[g])) continue;
         any = true;
-        if (iprof) { const long long t = clock64(); a.prof[48] += t - ti; ti = t; }     // time spent polling
+        if (iprof) { const long long t = clock64(); a.prof[96] += t - ti; ti = t; }     // time spent polling
         ph[g] ^= 1u;
         tc_fence_after();
         const int l = layer[g];
@@ -467,9 +461,12 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
         // so stepping to the next K-step / plane / chunk is one 32-bit add.  This warp's instruction stream paces the
         // narrow layers (an N = 32 MMA is 16 cycles of tensor time): no 64-bit arithmetic, division or descriptor
         // re-encoding inside the loops (ncu, first version: 40 % of the worker samples were waits on this warp).
-        const uint32_t idesc = lay_idesc[l], b_hi32 = (128u >> 4) | (1u << 14);
-        uint32_t b_h = lay_bh[l], b_l = lay_bl[l];
-        const uint32_t kinc = lay_kinc[l];
+        // per-layer constants straight from the kernel parameters (constant bank, indexed by l)
+        const int K = m.k[l], N = m.n[l];
+        const uint32_t idesc = make_idesc(128, N), b_hi32 = (128u >> 4) | (1u << 14);
+        const uint32_t wh = wreg_s + (uint32_t)m.woff[l];
+        uint32_t b_h = ((wh >> 4) & 0x3fffu) | ((uint32_t)N << 16), b_l = b_h + (uint32_t)((K * N * 2) >> 4);
+        const uint32_t kinc = (uint32_t)N * 2u;                 // 16 channels of the weight operand = N * 32 bytes (>> 4)
         const uint32_t t_acc = tmem_base + (uint32_t)(g * m.tg_cols);
         if (elect_one()) {
           if (l == 0) {
@@ -495,7 +492,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
             umma_bf16(t_acc, desc64(r_l, b_hi32), desc64(b_h, b_hi32), idesc, 1u);
           } else {
             uint32_t t_ahi = t_acc + (uint32_t)m.acc_cols, t_alo = t_ahi + (uint32_t)m.ta_cols;
-            const int ksteps = lay_ksteps[l];
+            const int ksteps = K / 16;
             umma_bf16_ts(t_acc, t_ahi, desc64(b_h, b_hi32), idesc, 0u);
             umma_bf16_ts(t_acc, t_ahi, desc64(b_l, b_hi32), idesc, 1u);
             umma_bf16_ts(t_acc, t_alo, desc64(b_h, b_hi32), idesc, 1u);
@@ -509,7 +506,7 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
           umma_commit(bar_acc0 + 8 * g);
         }
         __syncwarp();
-        if (iprof) { const long long t = clock64(); a.prof[49 + (l < 3 ? l : 3)] += t - ti; a.prof[53] += 1; ti = t; }   // time spent issuing layer l
+        if (iprof) { const long long t = clock64(); a.prof[97 + (l < 3 ? l : 3)] += t - ti; a.prof[101] += 1; ti = t; }   // time spent issuing layer l
       }
       if (any) idle = 0;
       else if (++idle > (1u << 26)) __trap();
@@ -543,8 +540,12 @@ static bool make_plan(Plan &m, int mode, int64_t C) {
     m.boff[l] = bf; bf += m.n[l];
   }
   m.wbytes = wb; m.bfloats = bf;
+  // TMEM column granularity of the A planes: 32 (SA1: 128 columns per group -> 4 groups of 128 threads, measured best: 0.250 ms);
+  // MVPNET_B200_TC2_TA_ALIGN=16 packs the hi / lo planes back to back (SA1: 96 columns -> 5 groups, 0.263 ms; results identical)
+  static const int ta_align = getenv("MVPNET_B200_TC2_TA_ALIGN") ? atoi(getenv("MVPNET_B200_TC2_TA_ALIGN")) : 32;
+  const int al = ta_align == 32 ? 32 : 16;
   m.acc_cols = (nmax + 31) & ~31;
-  m.ta_cols = ((kin / 2) + 31) & ~31;
+  m.ta_cols = ((kin / 2) + al - 1) & ~(al - 1);
   m.part_cols = mode == MODE_FA ? ((m.n[m.num_layers - 1] + 31) & ~31) : 0;
   m.tg_cols = m.acc_cols + 2 * m.ta_cols + m.part_cols;
   for (m.groups = MAXG; m.groups >= 1; --m.groups)
@@ -553,9 +554,9 @@ static bool make_plan(Plan &m, int mode, int64_t C) {
   return true;
 }
 
-template <int MODE, int NG>
+template <int MODE, int NG, int GT>
 static int launch_ng(const Args &a, Plan m, long long tiles, cudaStream_t stream) {
-  auto kern = tc2_kernel<MODE, NG>;
+  auto kern = tc2_kernel<MODE, NG, GT>;
   m.groups = NG;
   m.tmem_alloc = 32;
   while (m.tmem_alloc < NG * m.tg_cols) m.tmem_alloc <<= 1;
@@ -567,8 +568,8 @@ static int launch_ng(const Args &a, Plan m, long long tiles, cudaStream_t stream
   if (grid > want) grid = want;
   static const bool debug = getenv("MVPNET_B200_DEBUG") != nullptr;
   if (debug)
-    fprintf(stderr, "[tc2 mode=%d] tiles=%lld groups=%d grid=%lld smem=%zu nchunks=%d tmem=%d/%d wbytes=%d\n", MODE, tiles, NG, grid, smem, m.nchunks,
-            m.tg_cols, m.tmem_alloc, m.wbytes);
+    fprintf(stderr, "[tc2 mode=%d] tiles=%lld groups=%d x %d threads grid=%lld smem=%zu nchunks=%d tmem=%d/%d wbytes=%d\n", MODE, tiles, NG, GT, grid, smem,
+            m.nchunks, m.tg_cols, m.tmem_alloc, m.wbytes);
   kern<<<(unsigned)grid, NG * GT + 32, smem, stream>>>(a, m, tiles);
   return launch_status("tc2_fused_mlp");
 }
@@ -580,17 +581,24 @@ static int launch(const Args &a_in, const Plan &m, long long tiles, cudaStream_t
   Args a = a_in;
   static const bool want_prof = getenv("MVPNET_B200_TC2_PROF") != nullptr;
   if (want_prof) {                 // debug only: phase clocks of CTA 0, printed and reset by mvp_tc2_prof_dump()
-    if (g_prof == nullptr) { cudaMalloc(&g_prof, 64 * sizeof(long long)); cudaMemset(g_prof, 0, 64 * sizeof(long long)); }
+    if (g_prof == nullptr) { cudaMalloc(&g_prof, 128 * sizeof(long long)); cudaMemset(g_prof, 0, 128 * sizeof(long long)); }
     a.prof = g_prof;
   }
+  // m.groups = the most tile groups TMEM and shared memory allow (<= 6).  Up to 3 groups run 256 threads each; 4..6 groups run
+  // 128 threads each (MVPNET_B200_TC2_GROUPS caps the count: <= 3 selects the wide groups).
   int ng = m.groups;
   const long long per_sm = tiles / sm_count();
   if (per_sm < ng) ng = per_sm < 1 ? 1 : (int)per_sm;
   static const char *force = getenv("MVPNET_B200_TC2_GROUPS");
   if (force && atoi(force) >= 1 && atoi(force) < ng) ng = atoi(force);
-  if (ng == 3) return launch_ng<MODE, 3>(a, m, tiles, stream);
-  if (ng == 2) return launch_ng<MODE, 2>(a, m, tiles, stream);
-  return launch_ng<MODE, 1>(a, m, tiles, stream);
+  switch (ng) {
+    case 6: return launch_ng<MODE, 6, 128>(a, m, tiles, stream);
+    case 5: return launch_ng<MODE, 5, 128>(a, m, tiles, stream);
+    case 4: return launch_ng<MODE, 4, 128>(a, m, tiles, stream);
+    case 3: return launch_ng<MODE, 3, 256>(a, m, tiles, stream);
+    case 2: return launch_ng<MODE, 2, 256>(a, m, tiles, stream);
+    default: return launch_ng<MODE, 1, 256>(a, m, tiles, stream);
+  }
 }
 
 static int to_plan(const mvp_tc_chain_t *c, int mode, int64_t C, Plan *m) {
@@ -617,15 +625,15 @@ static int to_plan(const mvp_tc_chain_t *c, int mode, int64_t C, Plan *m) {
 
 extern "C" void mvp_tc2_prof_dump(const char *tag) {
   if (mvp::tc2::g_prof == nullptr) return;
-  long long h[64];
+  long long h[128];
   cudaDeviceSynchronize();
   cudaMemcpy(h, mvp::tc2::g_prof, sizeof(h), cudaMemcpyDeviceToHost);
   cudaMemset(mvp::tc2::g_prof, 0, sizeof(h));
   fprintf(stderr, "[tc2 prof %s] (cycles of CTA 0, summed over launches)\n", tag);
-  for (int g = 0; g < 3; ++g)
-    fprintf(stderr, "  group %d: wait_gather %lld  wait_L0 %lld  build %lld  epi0 %lld  wait_L1 %lld  epi1 %lld  wait_L2 %lld  epi2 %lld  wait_L3 %lld epi3 %lld\n", g,
+  for (int g = 0; g < 6; ++g)
+    if (h[g * 16 + 1]) fprintf(stderr, "  group %d: wait_gather %lld  wait_L0 %lld  build %lld  epi0 %lld  wait_L1 %lld  epi1 %lld  wait_L2 %lld  epi2 %lld  wait_L3 %lld epi3 %lld\n", g,
             h[g * 16], h[g * 16 + 1], h[g * 16 + 2], h[g * 16 + 3], h[g * 16 + 4], h[g * 16 + 5], h[g * 16 + 6], h[g * 16 + 7], h[g * 16 + 8], h[g * 16 + 9]);
-  fprintf(stderr, "  issuer: polling %lld  issue_L0 %lld  issue_L1 %lld  issue_L2 %lld  issue_L3+ %lld  requests %lld\n", h[48], h[49], h[50], h[51], h[52], h[53]);
+  fprintf(stderr, "  issuer: polling %lld  issue_L0 %lld  issue_L1 %lld  issue_L2 %lld  issue_L3+ %lld  requests %lld\n", h[96], h[97], h[98], h[99], h[100], h[101]);
 }
 
 extern "C" int mvp_tc2_supported(const mvp_tc_chain_t *c, int mode, int64_t C) {

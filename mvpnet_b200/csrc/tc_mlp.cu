@@ -58,6 +58,8 @@ struct Chain {
   int res_off[MAX_LAYERS];  // resident mode: byte offset of layer l's hi block (lo follows at + k*n*2)
   int res_bytes;
   int panel;              // K elements of the first layer built per pass (== k[0] unless the row is too wide for shared memory)
+  int bias_off[MAX_LAYERS];  // float offset of layer l's bias in the shared-memory copy
+  int bias_floats;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -416,6 +418,8 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
   unsigned char *aux_base = wreg + ((wreg_bytes + 127) & ~(size_t)127);
   uint64_t *bars = reinterpret_cast<uint64_t *>(aux_base + NG * AUX_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * MAX_STAGES + 2 * MAX_GROUPS);
+  // biases in shared memory (round 2: the per-chunk __ldg of the bias was 5 % of FP4's stall samples, all long-scoreboard)
+  float *bias_s = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(bars) + 256);
   const uint32_t bar_full0 = smem_u32(bars), bar_empty0 = smem_u32(bars + MAX_STAGES);
   const uint32_t bar_aready0 = smem_u32(bars + 2 * MAX_STAGES), bar_acc0 = smem_u32(bars + 2 * MAX_STAGES + MAX_GROUPS);
 
@@ -425,6 +429,8 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
     fence_barrier_init();
   }
   if (warp == NW) tmem_alloc(smem_u32(tmem_slot), (uint32_t)m.tmem_alloc);
+  for (int l = 0; l < m.num_layers; ++l)
+    for (int o = tid; o < m.n[l]; o += NTHREADS) bias_s[m.bias_off[l] + o] = __ldg(m.bias[l] + o);
   if (m.resident) {  // one cooperative copy of every layer's W_hi | W_lo for the lifetime of the CTA
     for (int l = 0; l < m.num_layers; ++l) {
       const size_t bytes = (size_t)m.k[l] * m.n[l] * 2;
@@ -497,10 +503,10 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
             if ((c + 2) * 16 < N) tmem_ld16_issue(t_lane + (uint32_t)((c + 2) * 16), rn);
-            const float4 *bp = reinterpret_cast<const float4 *>(m.bias[l] + c * 16);
+            const float4 *bp = reinterpret_cast<const float4 *>(bias_s + m.bias_off[l] + c * 16);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 bq = __ldg(bp + q);
+              const float4 bq = bp[q];
               add_pair(v[4 * q], v[4 * q + 1], bq.x, bq.y);
               add_pair(v[4 * q + 2], v[4 * q + 3], bq.z, bq.w);
             }
@@ -694,7 +700,7 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
 static size_t smem_bytes(const Chain &m) {
   const size_t a_bytes = (size_t)m.groups * (m.kmax >> 3) * SLAB * 2;
   const size_t w = m.resident ? (size_t)m.res_bytes : (size_t)m.stages * 2 * (m.kc >> 3) * m.nbmax * 16;
-  return a_bytes + ((w + 127) & ~(size_t)127) + m.groups * ((sizeof(Aux) + 127) & ~(size_t)127) + 256;
+  return a_bytes + ((w + 127) & ~(size_t)127) + m.groups * ((sizeof(Aux) + 127) & ~(size_t)127) + 256 + (((size_t)m.bias_floats * 4 + 127) & ~(size_t)127);
 }
 
 constexpr size_t SMEM_CAP = 227 * 1024;
@@ -704,7 +710,10 @@ static bool finalize(Chain &m, int mode, int fa_k) {
   m.nbmax = 0;
   int nmax = 0, kmax_rest = 0;
   size_t wbytes = 0;
+  m.bias_floats = 0;
   for (int l = 0; l < m.num_layers; ++l) {
+    m.bias_off[l] = m.bias_floats;
+    m.bias_floats += m.n[l];
     if (l > 0 && m.k[l] > kmax_rest) kmax_rest = m.k[l];
     const int nb = m.n[l] < 256 ? m.n[l] : 256;
     if (nb > m.nbmax) m.nbmax = nb;
