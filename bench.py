@@ -680,7 +680,28 @@ def main():
     try:
         e2e_mode['name'] = 'pipelined (engine.PipelinedForward: H2D / compute / D2H on separate streams, two buffer sets%s)' % (
             ', one compute lane per buffer set' if lanes > 1 else '')
-        fwd = [(lambda d, l=l: step_device(d, l)) for l in range(lanes)] if lanes > 1 else step_device
+        class LaneForward:
+            """Two-phase forward of one lane for engine.PipelinedForward: load() copies the uploaded batch into the lane's
+            captured static inputs (the upload buffers are then free), replay() runs the graph (+ the all-gather at N > 1)."""
+
+            def __init__(self, lane):
+                self.lane = lane
+                self.g = lane_graphs[lane] if lane_graphs else graphed['fn']
+
+            def load(self, d):
+                self.g.load(batch_of(d))
+
+            def replay(self):
+                with torch.no_grad():
+                    logit = self.g.replay()
+                    if world > 1:
+                        all_gather_chunks(logit, world * cpg, out=gathered[self.lane])
+                return logit
+
+        if lane_graphs or graphed['fn'] is not None:
+            fwd = [LaneForward(l) for l in range(lanes)] if lanes > 1 else LaneForward(0)
+        else:
+            fwd = [(lambda d, l=l: step_device(d, l)) for l in range(lanes)] if lanes > 1 else step_device
         pipe['p'] = engine.PipelinedForward(fwd, host, device, prepare=prepare, depth=2)
         for _ in range(2):
             step_e2e()

@@ -191,11 +191,19 @@ def _mlp_layers(shared_mlp):
 _CACHE = {}
 
 
+def _signature(module):
+    """What a packed copy of `module`'s weights depends on: identity and version of every parameter and buffer (in-place
+    updates bump `_version`, `.data = ...` reassignment changes `data_ptr`), the device, and whether ANY sub-module is in
+    training mode.  Walks parameters() / buffers() directly — state_dict() builds 426 prefixed keys per call."""
+    sig = [(t.data_ptr(), int(t._version)) for t in module.parameters()]
+    sig += [(t.data_ptr(), int(t._version)) for t in module.buffers()]
+    return tuple(sig), next(module.parameters()).device, any(m.training for m in module.modules())
+
+
 def _cached(module, key, build):
     """Per-module cache of packed weights / plans.  Keyed by id(module) AND checked against a weak reference: ids are
     reused after garbage collection, and a stale hit would silently run another model's weights."""
-    sig = (key, tuple(int(t._version) for t in module.state_dict().values()),
-           next(module.parameters()).device, module.training)
+    sig = (key,) + _signature(module)
     hit = _CACHE.get((id(module), key))
     if hit is None or hit[0] != sig or hit[2]() is not module:
         hit = (sig, build(), weakref.ref(module))
@@ -205,8 +213,14 @@ def _cached(module, key, build):
     return hit[1]
 
 
+def invalidate(module=None):
+    """Drop the packed weights of `module` (or of every module): they are rebuilt on the next fused forward."""
+    for k in [k for k in _CACHE if module is None or k[0] == id(module)]:
+        del _CACHE[k]
+
+
 def _require_eval_fp32(module, *tensors):
-    if module.training:
+    if any(m.training for m in module.modules()):      # a sub-module left in train() would get its BatchNorm folded with running statistics
         raise RuntimeError('mvpnet_b200 fused path is inference-only (BatchNorm folded): call .eval() or use forward()')
     for t in tensors:
         if t is not None and (not t.is_cuda or t.dtype != torch.float32):
@@ -366,7 +380,7 @@ def pn2ssg_forward(net, data_batch):
 # MVPNet3D
 # ------------------------------------------------------------------------------------------------
 class _Streams:
-    geo = None
+    geo = {}          # one side stream per device (a process-global stream would silently serialise a second GPU's forward)
 
 
 FOLD_NET2D_BN = os.environ.get('MVPNET_B200_FOLD_BN', '1') == '1'
@@ -448,9 +462,10 @@ def mvpnet3d_forward(model, data_batch, overlap=True):
         return rg, pn2_geometry(net3d, xyz_pm)
 
     if overlap:
-        if _Streams.geo is None:
-            _Streams.geo = torch.cuda.Stream()
-        side = _Streams.geo
+        dev_index = images.device.index if images.device.index is not None else torch.cuda.current_device()
+        if dev_index not in _Streams.geo:
+            _Streams.geo[dev_index] = torch.cuda.Stream(device=images.device)
+        side = _Streams.geo[dev_index]
         side.wait_stream(main)                     # orders reuse of last call's buffers, keeps overlap
         with torch.cuda.stream(side):
             rg, geo = coordinate_work()
@@ -475,6 +490,10 @@ def mvpnet3d_forward(model, data_batch, overlap=True):
         feat2d = feat2d.view(b, nv, *feat2d.shape[1:])
     if overlap:
         main.wait_stream(side)
+        if not torch.cuda.is_current_stream_capturing():      # (a captured graph owns its private pool: nothing is reused inside it)
+            for t in list(geo['xyz']) + list(geo['nbr']) + [x for pair in geo['knn'] for x in pair] + [rg['image_xyz'], rg['knn_indices']]:
+                if torch.is_tensor(t):
+                    t.record_stream(main)  # allocated on the side stream, consumed on the caller's: keep the allocator from reusing them early
     if rows:
         _, fa_split = feature_aggregation_rows(fa, pix_split, nv, h, w, rg['image_xyz'], rg['knn_indices'], points)
         return {'seg_logit': pn2_features(net3d, geo, None, fa_split)}
@@ -530,12 +549,20 @@ class GraphedForward:
         with torch.no_grad(), torch.cuda.graph(self.graph):
             self.static_out = model.fast_forward(self.static_in)['seg_logit']
 
-    def __call__(self, batch):
+    def load(self, batch):
+        """Phase 1: copy the batch into the captured static input buffers (the caller's tensors are free afterwards)."""
         for k, v in batch.items():
             if torch.is_tensor(v):
                 self.static_in[k].copy_(v, non_blocking=True)
+
+    def replay(self):
+        """Phase 2: replay the graph on the loaded inputs; returns the static output tensor."""
         self.graph.replay()
         return self.static_out
+
+    def __call__(self, batch):
+        self.load(batch)
+        return self.replay()
 
 
 class PipelinedForward:
@@ -581,8 +608,17 @@ class PipelinedForward:
                 compute.wait_stream(caller)               # first use of the lane: order after the caller's set-up work
             compute.wait_event(self.in_ready[s])
             dev = self.slots[s]
-            out = fwd(self.prepare(dev) if self.prepare is not None else dev)
-            self.in_free[s].record(compute)
+            batch = self.prepare(dev) if self.prepare is not None else dev
+            if hasattr(fwd, 'load') and hasattr(fwd, 'replay'):
+                # two-phase forwards (GraphedForward) copy the inputs into their own static buffers first: the upload buffers
+                # are free as soon as that copy is queued, so the NEXT upload into this slot overlaps this forward instead
+                # of waiting for it to end (measured: the lane idled ~0.5 ms per step waiting for its upload)
+                fwd.load(batch)
+                self.in_free[s].record(compute)
+                out = fwd.replay()
+            else:
+                out = fwd(batch)
+                self.in_free[s].record(compute)
             if self.out_dev[s] is None:
                 self.out_dev[s] = torch.empty_like(out)
                 self.out_host[s] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
