@@ -404,7 +404,9 @@ __device__ __forceinline__ void issue_kstep(uint32_t d_tmem, uint32_t a_hi, uint
 constexpr int FA_PSTRIDE = 33;
 
 template <int MODE, int NG>
-__global__ void __launch_bounds__(NG *GROUP_THREADS + CTRL_THREADS, 1)
+// single-group CTAs are compiled for TWO per SM (<= 96 registers): two independent CTAs de-phase naturally, so one's MMA
+// phase overlaps the other's build / epilogue (the groups of one CTA advance in lock step around the shared weight ring)
+__global__ void __launch_bounds__(NG *GROUP_THREADS + CTRL_THREADS, NG == 1 ? 2 : 1)
 tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, long long num_tiles) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -804,6 +806,21 @@ static int launch(const BuildArgs &a, Chain m, float *out, long long tiles, cuda
       }
     }
   }
+  // Streamed-weight chains: TWO single-group CTAs per SM where a tile + a two-stage ring fit twice (FP4: 107 KB, 128 TMEM
+  // columns, 96 registers) instead of one CTA with two lock-stepped groups.  Independent CTAs de-phase, so one's MMA phase
+  // overlaps the other's gather / epilogue: FP4 0.288 -> 0.239 ms (each CTA streams its own weights; the ring depth was
+  // measured irrelevant: 2 or 5 stages, same time).  MVPNET_B200_TC_TWO_CTAS=0 keeps the grouped form.
+  static const bool two_ctas = getenv("MVPNET_B200_TC_TWO_CTAS") == nullptr || getenv("MVPNET_B200_TC_TWO_CTAS")[0] != '0';
+  if (two_ctas && !m.resident && ng >= 2 && m.tmem_cols <= 256 && tiles >= 4LL * sm_count()) {
+    Chain t = m;
+    t.groups = 1;
+    t.stages = 2;
+    t.tmem_alloc = 32;
+    while (t.tmem_alloc < t.tmem_cols) t.tmem_alloc <<= 1;
+    if (2 * (smem_bytes(t) + 1024) <= SMEM_CAP) return launch_ng<MODE, 1>(a, t, out, tiles, stream);
+  }
+  static const char *cap = getenv("MVPNET_B200_TC_STAGES_CAP");     // experiment knob
+  if (cap && !m.resident && atoi(cap) >= 2 && atoi(cap) < m.stages) m.stages = atoi(cap);
   if (ng == 3) return launch_ng<MODE, 3>(a, m, out, tiles, stream);
   if (ng == 2) return launch_ng<MODE, 2>(a, m, out, tiles, stream);
   return launch_ng<MODE, 1>(a, m, out, tiles, stream);
