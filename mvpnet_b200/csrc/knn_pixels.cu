@@ -49,13 +49,16 @@ __device__ __forceinline__ void topk_insert(double d, int id, double (&bd)[KMAX]
   }
 }
 
+// warp arg-min of (d, i), lexicographic; d >= 0 or +inf, so its bit pattern orders like an unsigned 64-bit integer:
+// three `redux.sync` (high word, low word among the minima, index among those) instead of a shuffle butterfly
 __device__ __forceinline__ void warp_argmin_d(double &d, int &i) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double od = __shfl_xor_sync(0xffffffffu, d, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (od < d || (od == d && oi < i)) { d = od; i = oi; }
-  }
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+  const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  const unsigned r = __reduce_min_sync(0xffffffffu, hi == mh && lo == ml ? (unsigned)i : 0xffffffffu);
+  d = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  i = (int)r;
 }
 
 // ------------------------------------------------------------------------------------------------

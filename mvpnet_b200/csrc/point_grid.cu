@@ -346,14 +346,30 @@ __device__ __forceinline__ void pg_top3_insert(T d, int j, T (&bd)[3], int (&bi)
   }
 }
 
+// Warp arg-min of (d, i), lexicographic, every lane gets the result.  d is a squared distance or +inf (non-negative, so
+// its bit pattern orders like an unsigned integer), i a key index or the 0x7fffffff sentinel: two (float) / three
+// (double) `redux.sync` instead of a 5-step shuffle butterfly with a two-key compare — the ncu source view of
+// pg_knn3_kernel (profiles/r2_knn3_lines.txt) had 20 % of its samples and 18 % of its instructions in that butterfly
+// (the kernel is issue-bound: 86 % SM busy, 1437 instructions per query).
 template <typename T>
-__device__ __forceinline__ void pg_warp_argmin(T &d, int &i) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const T od = __shfl_xor_sync(0xffffffffu, d, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    if (od < d || (od == d && oi < i)) { d = od; i = oi; }
-  }
+__device__ __forceinline__ void pg_warp_argmin(T &d, int &i);
+template <>
+__device__ __forceinline__ void pg_warp_argmin<float>(float &d, int &i) {
+  const unsigned db = __float_as_uint(d);
+  const unsigned m = __reduce_min_sync(0xffffffffu, db);
+  const unsigned r = __reduce_min_sync(0xffffffffu, db == m ? (unsigned)i : 0xffffffffu);
+  d = __uint_as_float(m);
+  i = (int)r;
+}
+template <>
+__device__ __forceinline__ void pg_warp_argmin<double>(double &d, int &i) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+  const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+  const unsigned r = __reduce_min_sync(0xffffffffu, hi == mh && lo == ml ? (unsigned)i : 0xffffffffu);
+  d = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+  i = (int)r;
 }
 
 template <typename T>

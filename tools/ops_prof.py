@@ -1,5 +1,6 @@
 """The six extension ops + unprojection + pixel k-NN at the model's shapes (32 chunks), one call each: the target of
 `ncu --set full` for per-kernel achieved DRAM GB/s (VERDICT r1 missing #6).  Also prints CUDA-event times."""
+import os
 import sys
 import numpy as np
 import torch
@@ -20,7 +21,12 @@ cam_inv = rep(lambda c: np.broadcast_to(invert_intrinsics(c['cam_matrix']), (5, 
 box = rep(lambda c: c['chunk_box'])
 
 
+ONCE = os.environ.get('MVPNET_OPS_ONCE') == '1'      # one launch per op (under ncu)
+
+
 def t(name, fn, n=5):
+    if ONCE:
+        return fn()
     fn()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -49,3 +55,8 @@ with torch.no_grad():
     o = t('interpolate fwd 128ch 2048->8192', lambda: ext.interpolate_cuda.interpolate_forward(f2, ki, w))
     t('interpolate bwd (atomic)', lambda: ext.interpolate_cuda.interpolate_backward(o, ki, w, 2048))
     t('interpolate bwd (deterministic)', lambda: ext.interpolate_cuda.interpolate_backward_det(o, ki, w, 2048))
+from mvpnet_b200 import train  # noqa: E402
+lg = torch.randn(B, 20, 8192, device=dev, requires_grad=True)
+lb = torch.randint(0, 20, (B, 8192), device=dev)
+t('seg_loss fwd (loss + confusion)', lambda: train.seg_loss_and_confusion(lg, lb))
+t('seg_loss fwd + bwd', lambda: train.seg_loss_and_confusion(lg, lb)[0].backward())
