@@ -334,6 +334,11 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
     }
   };
 
+  // distance from the query to the low / high face planes of its own cell (shell 0)
+  const double face_lo[3] = {__dsub_rn(qx, __dadd_rn(g.ox, __dmul_rn((double)cx, g.s))), __dsub_rn(qy, __dadd_rn(g.oy, __dmul_rn((double)cy, g.s))),
+                             __dsub_rn(qz, __dadd_rn(g.oz, __dmul_rn((double)cz, g.s)))};
+  const double face_hi[3] = {__dsub_rn(__dadd_rn(g.ox, __dmul_rn((double)(cx + 1), g.s)), qx), __dsub_rn(__dadd_rn(g.oy, __dmul_rn((double)(cy + 1), g.s)), qy),
+                             __dsub_rn(__dadd_rn(g.oz, __dmul_rn((double)(cz + 1), g.s)), qz)};
   double kth = Inf<double>::v();   // k-th best squared distance over the whole warp so far
   for (int r = 0; r <= rmax; ++r) {
     // Shell r = the (y, z) positions of a (2r+1)^2 square; a position on the square's rim contributes its
@@ -341,12 +346,14 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
     // Lanes fetch the run boundaries of 32 positions at once (the dependent loads are the latency of this
     // kernel), then the warp streams the non-empty runs cooperatively.
     const int side = 2 * r + 1, npos = side * side;
+    const float inv_side = __fdividef(1.0f, (float)side);
     const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
     for (int base = 0; base < npos; base += 32) {
       const int t = base + lane;
       int beg0 = 0, end0 = 0, beg1 = 0, end1 = 0;
       if (t < npos) {
-        const int dz = t / side - r, dy = t - (t / side) * side - r;
+        const int tq = side <= 255 ? (int)__fmul_rn((float)t + 0.5f, inv_side) : t / side;   // floor(t / side), exact for small t
+        const int dz = tq - r, dy = t - tq * side - r;
         const int z = cz + dz, y = cy + dy;
         if (z >= 0 && z < g.gz && y >= 0 && y < g.gy) {
           const int row = (z * g.gy + y) * g.gx;
@@ -385,14 +392,17 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
     }
     // Every pixel outside the visited cube [c-r, c+r]^3 lies beyond one of the cube's faces that still has
     // cells behind it; its distance is at least the distance from the query to that face plane.
+    // The face planes move outwards by one cell edge per shell: distance = (distance at r = 0) + r * s.  Two operations per
+    // face instead of five (this was 9 % of the kernel's instructions); the rounding of either form (~1e-13 of the bound)
+    // is far inside the 1e-9 margin of the stop rule below.
     double bound = Inf<double>::v();
     {
-      const double qv[3] = {qx, qy, qz}, ov[3] = {g.ox, g.oy, g.oz};
+      const double rs = __dmul_rn((double)r, g.s);
       const int cv[3] = {cx, cy, cz}, gv[3] = {g.gx, g.gy, g.gz};
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        if (cv[a] - r > 0) bound = fmin(bound, __dsub_rn(qv[a], __dadd_rn(ov[a], __dmul_rn((double)(cv[a] - r), g.s))));
-        if (cv[a] + r + 1 < gv[a]) bound = fmin(bound, __dsub_rn(__dadd_rn(ov[a], __dmul_rn((double)(cv[a] + r + 1), g.s)), qv[a]));
+        if (cv[a] - r > 0) bound = fmin(bound, __dadd_rn(face_lo[a], rs));
+        if (cv[a] + r + 1 < gv[a]) bound = fmin(bound, __dadd_rn(face_hi[a], rs));
       }
     }
     if (bound > 0.0 && kth < __dmul_rn(__dmul_rn(bound, bound), 1.0 - 1e-9)) break;

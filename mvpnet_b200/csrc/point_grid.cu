@@ -404,12 +404,14 @@ pg_knn3_kernel(const T *__restrict__ query, const PgGrid<T> *__restrict__ grids,
     // shell r: the (y, z) positions of a (2r+1)^2 square; a rim position contributes its whole x extent (one run),
     // an interior position its two end cells.  Lanes fetch the run boundaries of 32 positions at once.
     const int side = 2 * r + 1, npos = side * side;
+    const float inv_side = __fdividef(1.0f, (float)side);
     const int x0 = max(cx - r, 0), x1 = min(cx + r, g.gx - 1);
     for (int base = 0; base < npos; base += 32) {
       const int t = base + lane;
       int beg0 = 0, end0 = 0, beg1 = 0, end1 = 0;
       if (t < npos) {
-        const int dz = t / side - r, dy = t - (t / side) * side - r;
+        const int tq = side <= 255 ? (int)__fmul_rn((float)t + 0.5f, inv_side) : t / side;   // floor(t / side) without an integer division (exact: checked exhaustively)
+        const int dz = tq - r, dy = t - tq * side - r;
         const int z = cz + dz, y = cy + dy;
         if (z >= 0 && z < g.gz && y >= 0 && y < g.gy) {
           const int row = (z * g.gy + y) * g.gx;
