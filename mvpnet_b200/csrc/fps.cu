@@ -61,8 +61,8 @@ __device__ __forceinline__ unsigned morton3(unsigned x, unsigned y, unsigned z) 
 // N = 2048 runs 0.29 us / iteration plain, 0.40 us bucketed): identity order, thread t owns j = t + p * T with T a
 // multiple of the reference BLOCK, so the first strict maximum in p order IS the reference's tie order and no
 // per-point rank is kept.
-template <int PPT, bool BUCKET>
-__global__ void __launch_bounds__(1024, 1)
+template <int PPT, bool BUCKET, int MAXT = 1024>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_regs_kernel(const float *__restrict__ points, int64_t *__restrict__ index, int N, int M, int lg) {
   extern __shared__ float s_xyz[];  // [N*3] AoS mirror (ORIGINAL order) for the centroid broadcast, then u16 perm[N]
   __shared__ unsigned s_part_d[2][32];
@@ -761,10 +761,22 @@ extern "C" int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int6
     return launch_status("fps");
   }
   if (fits_regs(N, D, dtype)) {
-    // bucketed (N >= 4096): every point carries its tie rank, the launch geometry is free: 1024 threads.
-    // plain: T must be a multiple of the reference BLOCK (= 1 << lg, <= 512) for the p-order tie rule (see the kernel).
-    const bool bucket = N >= 4096;
-    int threads = bucket ? 1024 : ((1 << lg) < 32 ? 32 : (1 << lg));
+    // Bucketed kernel: 16 points per thread, i.e. 16 warps at N = 8192.  Once the distance work is pruned, what is left of an
+    // iteration is the ISSUE cost of the common path every warp executes (centroid read, box test, barrier, block arg-max:
+    // ~60 instructions): measured at N = 8192, 32 clouds: 32 warps x 8 points 0.640 us / iteration, 16 x 16 0.418 us,
+    // 8 x 32 0.515 us (fewer warps, but each active warp then scans 32 points per lane).
+    static const long long bucket_min = getenv("MVPNET_B200_FPS_BUCKET_MIN") ? atoll(getenv("MVPNET_B200_FPS_BUCKET_MIN")) : 4096;
+    const bool bucket = N >= bucket_min;
+    if (bucket) {
+      int threads16 = (int)((N + 15) / 16);
+      threads16 = (threads16 + 31) / 32 * 32;
+      const size_t smem16 = (size_t)N * 3 * sizeof(float) + (size_t)N * sizeof(unsigned short);
+      cudaFuncSetAttribute(fps_regs_kernel<16, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+      fps_regs_kernel<16, true, 512><<<(unsigned)B, threads16, smem16, stream>>>((const float *)points, index, (int)N, (int)M, lg);
+      return launch_status("fps");
+    }
+    // plain kernel: T must be a multiple of the reference BLOCK (= 1 << lg, <= 512) for the p-order tie rule (see the kernel)
+    int threads = (1 << lg) < 32 ? 32 : (1 << lg);
     while (threads < 1024 && (N + threads - 1) / threads > 8) threads *= 2;
     int ppt = (int)((N + threads - 1) / threads);
     ppt = ppt <= 1 ? 1 : ppt <= 2 ? 2 : ppt <= 4 ? 4 : 8;
@@ -775,15 +787,11 @@ extern "C" int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int6
     cudaFuncSetAttribute(fps_regs_kernel<P, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     fps_regs_kernel<P, BK><<<(unsigned)B, threads, smem, stream>>>(p, index, (int)N, (int)M, lg);     \
   } while (0)
-    if (bucket) {
-      if (ppt <= 4) MVP_FPS_LAUNCH(4, true); else MVP_FPS_LAUNCH(8, true);
-    } else {
-      switch (ppt) {
-        case 1: MVP_FPS_LAUNCH(1, false); break;
-        case 2: MVP_FPS_LAUNCH(2, false); break;
-        case 4: MVP_FPS_LAUNCH(4, false); break;
-        default: MVP_FPS_LAUNCH(8, false); break;
-      }
+    switch (ppt) {
+      case 1: MVP_FPS_LAUNCH(1, false); break;
+      case 2: MVP_FPS_LAUNCH(2, false); break;
+      case 4: MVP_FPS_LAUNCH(4, false); break;
+      default: MVP_FPS_LAUNCH(8, false); break;
     }
 #undef MVP_FPS_LAUNCH
     return launch_status("fps");
