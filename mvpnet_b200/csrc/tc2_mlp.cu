@@ -95,13 +95,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): fewer wake-ups that only re-issue the wait
         : "memory");
-    if (!ok && ++spins > (1u << 22)) __trap();
+    if (!ok && ++spins > (1u << 20)) __trap();
   } while (!ok);
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -396,17 +396,17 @@ tc2_kernel(const Args a, const Plan m, long long num_tiles) {
             if (cur.slot == passes - 1 && pid < a.rows_out) {
               const size_t o = (size_t)pid * m.out_channels + c * 16;
               if (a.out_f32 != nullptr) {
-                float4 *op = reinterpret_cast<float4 *>(a.out_f32 + o);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 2; ++q)       // 256-bit stores: whole L2 sectors per instruction
+                  st_global_256(a.out_f32 + o + 8 * q, make_uint4(__float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3])),
+                                make_uint4(__float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7])));
               }
               if (a.out_hi != nullptr) {
                 uint32_t h[8], lo[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], lo[q]);
-                uint4 *oh = reinterpret_cast<uint4 *>(a.out_hi + o), *ol = reinterpret_cast<uint4 *>(a.out_lo + o);
-                oh[0] = make_uint4(h[0], h[1], h[2], h[3]); oh[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                ol[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); ol[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                st_global_256(a.out_hi + o, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
+                st_global_256(a.out_lo + o, make_uint4(lo[0], lo[1], lo[2], lo[3]), make_uint4(lo[4], lo[5], lo[6], lo[7]));
               }
             }
           }
@@ -681,6 +681,8 @@ extern "C" int mvp_tc2_feature_aggregation(const void *pix_hi, const void *pix_l
               "tc2_feature_aggregation: null pointer");
   MVP_REQUIRE((((uintptr_t)pix_hi | (uintptr_t)pix_lo | (uintptr_t)out_f32 | (uintptr_t)out_hi | (uintptr_t)out_lo) & 15) == 0, MVP_ERR_INVALID_ARG,
               "tc2_feature_aggregation: pointers must be 16-byte aligned");
+  MVP_REQUIRE((((uintptr_t)out_f32 | (uintptr_t)out_hi | (uintptr_t)out_lo) & 31) == 0, MVP_ERR_INVALID_ARG,
+              "tc2_feature_aggregation: outputs must be 32-byte aligned (256-bit stores)");
   tc2::Args a = {};
   a.rows_out = B * Np; a.src_hi = (const __nv_bfloat16 *)pix_hi; a.src_lo = (const __nv_bfloat16 *)pix_lo; a.C = (int)C;
   a.xyz = pix_xyz; a.new_xyz = points; a.nbr = knn; a.n_src = (unsigned)(nv * h * w); a.n_out = (unsigned)Np; a.k = (int)K;

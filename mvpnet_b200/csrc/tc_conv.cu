@@ -288,17 +288,18 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
               }
             }
             if (a.out_f != nullptr) {
-              float4 *op = reinterpret_cast<float4 *>(a.out_f + cur.fbase + c);
+              float *op = a.out_f + cur.fbase + c;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 0; q < 2; ++q)
+                st_global_256(op + 8 * q, make_uint4(__float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3])),
+                              make_uint4(__float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7])));
             }
             if (a.out_rh != nullptr) {   // what the fused FeatureAggregation gathers: pixel-major rows, already split
               uint32_t h[8], l[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
-              uint4 *oh = reinterpret_cast<uint4 *>(a.out_rh + cur.fbase + c), *ol = reinterpret_cast<uint4 *>(a.out_rl + cur.fbase + c);
-              oh[0] = make_uint4(h[0], h[1], h[2], h[3]); oh[1] = make_uint4(h[4], h[5], h[6], h[7]);
-              ol[0] = make_uint4(l[0], l[1], l[2], l[3]); ol[1] = make_uint4(l[4], l[5], l[6], l[7]);
+              st_global_256(a.out_rh + cur.fbase + c, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
+              st_global_256(a.out_rl + cur.fbase + c, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
             }
           }
         }
@@ -607,6 +608,8 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
   MVP_REQUIRE(x1 && w_packed && bias && (out_planar || out_nhwc || out_rows) && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3: null pointer");
   MVP_REQUIRE((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)out_planar |
                 (uintptr_t)out_nhwc | (uintptr_t)out_rows) & 15) == 0, MVP_ERR_INVALID_ARG, "tc_conv3x3: pointers must be 16-byte aligned");
+  MVP_REQUIRE((((uintptr_t)out_nhwc | (uintptr_t)out_rows) & 31) == 0, MVP_ERR_INVALID_ARG,
+              "tc_conv3x3: the NHWC / row-split outputs must be 32-byte aligned (256-bit stores)");
   tcc::ConvArgs a = {};
   const int pair = H <= 8 ? 1 : 0;
   const int64_t Np = pair ? (N + 1) / 2 * 2 : N;

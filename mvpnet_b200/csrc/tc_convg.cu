@@ -24,7 +24,8 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map
 
 constexpr int G_MAX_TAPS = 9;
 constexpr int G_MAX_STAGES = 6;
-constexpr int G_EPI_THREADS = 128, G_THREADS = G_EPI_THREADS + 96;
+constexpr int G_EPI_WARPS = 8;                  // two per TMEM lane quarter: alternate 16-column chunks (as tc_conv.cu)
+constexpr int G_EPI_THREADS = G_EPI_WARPS * 32, G_THREADS = G_EPI_THREADS + 96;
 
 struct ConvGArgs {
   CUtensorMap mh, ml;               // input planes
@@ -48,6 +49,7 @@ struct ConvGArgs {
   int TX, TY;
   long long ntiles, ngroups;
   int TM, nacc, astages, stages, tmem_cols;
+  int resident;                     // the whole weight block lives in the `stages` (= K-loop length) stages: loaded once per CTA
   unsigned int *sched;              // dynamic work distribution counters (tc_conv.cu)
 };
 
@@ -79,7 +81,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
     for (int s = 0; s < SCHED_DEPTH; ++s) { mbar_init(bar_sfull + 8 * s, 1); mbar_init(bar_sempty + 8 * s, 2 + G_EPI_THREADS / 32); }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == G_EPI_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   for (int i = tid; i < a.Cout; i += G_THREADS) s_bias[i] = a.bias[i];
   tc_fence_before();
   __syncthreads();
@@ -91,12 +93,16 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
   const int per_img = a.TX * a.TY;
   const int iters = a.nchunks * a.ntaps;                         // K-loop length of one work item
 
-  if (warp < 4) {
-    // =========================== epilogue ============================================================================
-    const int row = warp * 32 + lane, g = row >> 3, xx = row & 7;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  if (warp < G_EPI_WARPS) {
+    // =========================== epilogue: thread = TMEM lane = pixel; the two warps of a lane quarter take alternate
+    //                             16-column chunks (the transposed convolutions are epilogue-paced: 256 columns per K = 64) ===
+    const int quarter = warp & 3, c0 = (warp >> 2) * 16;
+    const int row = quarter * 32 + lane, g = row >> 3, xx = row & 7;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int C8o = a.Cout >> 3, out_pair = a.Ho <= 8;
     const size_t slab_stride = (size_t)a.Ho * a.Wo * 8 * (out_pair ? 2 : 1);
+    const bool paired = a.shuffle && 2 * a.Cout <= a.Nt;         // a block holds whole (kx = 0, kx = 1) parity pairs
+    const int cpc = a.Cout >> 4, npair = a.Nt >> 5;              // 16-column chunks per parity; paired items per tile
     for (uint32_t it = 0;; ++it) {
       const int w = sched_consume(it, s_ring, bar_sfull, bar_sempty);
       if (w >= nworks) break;
@@ -112,14 +118,57 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
         const int yr = (r / a.TX) * 16 + g, xr = (r % a.TX) * 8 + xx;
         const bool ok = yr < a.Hr && xr < a.Wr;
         const uint32_t t_acc = t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
+        if (paired) {
+          // transposed convolution, both x parities of an output row in this block: an item = 16 channels of one y
+          // parity, the two x parities side by side -> 32 contiguous bytes per (slab, plane), one STG.256 each
+          for (int j = c0 >> 4; j < npair; j += 2) {
+            const int kyl = j / cpc, cc = j - kyl * cpc;
+            const int col = kyl * 2 * a.Cout + cc * 16, gcol = nb * a.Nt + col;
+            const int par = gcol / a.Cout, co = gcol - par * a.Cout;           // par even: (ky, kx = 0)
+            uint32_t ra[16], rb[16];
+            tmem_ld16_issue(t_acc + (uint32_t)col, ra);
+            tmem_ld16_issue(t_acc + (uint32_t)(col + a.Cout), rb);
+            const size_t pbase = ok ? planar_off(n, co >> 3, 2 * yr + (par >> 1), 2 * xr, C8o, a.Ho, a.Wo, out_pair) : 0;
+            float bq[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = reinterpret_cast<const float4 *>(s_bias + co)[q];
+              bq[4 * q] = b4.x; bq[4 * q + 1] = b4.y; bq[4 * q + 2] = b4.z; bq[4 * q + 3] = b4.w;
+            }
+            tmem_ld_wait(ra);
+            tmem_ld_wait(rb);
+            float va[16], vb[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              va[q] = __uint_as_float(ra[q]) + bq[q];
+              vb[q] = __uint_as_float(rb[q]) + bq[q];
+              if (a.relu) { va[q] = fmaxf(va[q], 0.f); vb[q] = fmaxf(vb[q], 0.f); }
+            }
+            if (ok) {
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                uint32_t ha[4], la[4], hb[4], lb[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  split_pair(va[8 * s + 2 * q], va[8 * s + 2 * q + 1], ha[q], la[q]);
+                  split_pair(vb[8 * s + 2 * q], vb[8 * s + 2 * q + 1], hb[q], lb[q]);
+                }
+                const size_t o = pbase + (size_t)s * slab_stride;
+                st_global_256(a.out_p + o, make_uint4(ha[0], ha[1], ha[2], ha[3]), make_uint4(hb[0], hb[1], hb[2], hb[3]));
+                st_global_256(a.out_p + a.plane_out + o, make_uint4(la[0], la[1], la[2], la[3]), make_uint4(lb[0], lb[1], lb[2], lb[3]));
+              }
+            }
+          }
+          continue;
+        }
         uint32_t rn[16];
-        tmem_ld16_issue(t_acc, rn);
-        for (int c = 0; c < a.Nt; c += 16) {
+        if (c0 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)c0, rn);
+        for (int c = c0; c < a.Nt; c += 32) {
           float v[16];
           tmem_ld_wait(rn);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
-          if (c + 16 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 16), rn);
+          if (c + 32 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 32), rn);
           // GEMM column -> (parity, output channel): a 16-column chunk never straddles a parity (Cout % 16 == 0)
           const int col = nb * a.Nt + c;
           const int par = a.shuffle ? col / a.Cout : 0, co = a.shuffle ? col - par * a.Cout : col;
@@ -151,7 +200,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       tc_fence_before();
       mbar_arrive(bar_accempty + 8 * set);
     }
-  } else if (warp == 4) {
+  } else if (warp == G_EPI_WARPS) {
     // =========================== MMA issuer (whole warp walks, one elected lane issues) ==============================
     // running ring positions / phases and 32-bit descriptor arithmetic only: see tc_conv.cu
     const uint32_t idesc = make_idesc(128, a.Nt);
@@ -174,7 +223,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       uint32_t first = 0u;
       for (int i = 0; i < iters; ++i) {
         mbar_wait(bar_afull + 8 * sa, a_ph);
-        mbar_wait(bar_bfull + 8 * sb, b_ph);
+        mbar_wait(bar_bfull + 8 * sb, a.resident ? 0u : b_ph);       // resident: phase 0 completes once and stays complete
         const uint32_t a_lo = a_lo0 + sa * a_stage16, b_lo = b_lo0 + sb * b_stage16;
         if (elect_one()) {
 #pragma unroll
@@ -194,7 +243,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
               }
             }
           }
-          umma_commit(bar_bempty + 8 * sb);
+          if (!a.resident) umma_commit(bar_bempty + 8 * sb);
           umma_commit(bar_aempty + 8 * sa);
           if (i == iters - 1) umma_commit(bar_accfull + 8 * set);
         }
@@ -205,7 +254,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       }
       if (++set == NA) { set = 0; acc_ph ^= 1u; }
     }
-  } else if (warp == 5) {
+  } else if (warp == G_EPI_WARPS + 1) {
     // =========================== input producer: one TMA box per (tile, chunk, tap, plane) ===========================
     const uint32_t a_s = smem_u32(a_base);
     const int C8 = a.Cin >> 3, kslabs = a.KC >> 3;
@@ -269,6 +318,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
       if (w >= nworks) break;
       const int nb = w / ngroups;
       const unsigned char *wsrc = a.wp + (size_t)nb * nch16 * a.ntaps * b_piece;
+      if (a.resident && k > 0) continue;                    // every stage was filled for the first work item and is never released
       for (int c = 0; c < a.nchunks; ++c) {
         for (int tap = 0; tap < a.ntaps; ++tap, ++it) {
           if (it >= S) mbar_wait(bar_bempty + 8 * s, ph ^ 1u);
@@ -285,7 +335,7 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  if (warp == G_EPI_WARPS) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 // ---- stem helper: fp32 NCHW image (3 channels) -> split-planar "row-unfolded" tensor with 32 channels per pixel:
@@ -408,6 +458,7 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   MVP_REQUIRE(N * Ho * Wo < (1LL << 31) && N * Hi * Wi < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv_general: more than 2^31 pixels");
   if (N == 0) return 0;
   MVP_REQUIRE(x && w_packed && bias && out_planar, MVP_ERR_NULL, "tc_conv_general: null pointer");
+  MVP_REQUIRE(((uintptr_t)out_planar & 31) == 0, MVP_ERR_INVALID_ARG, "tc_conv_general: the output must be 32-byte aligned (256-bit stores)");
   tcc::ConvGArgs a = {};
   a.Cin = (int)Cin; a.N = (int)N; a.Hi = (int)Hi; a.Wi = (int)Wi; a.Ho = (int)Ho; a.Wo = (int)Wo;
   a.shuffle = mode; a.stride = stride; a.ntaps = ntaps;
@@ -426,6 +477,17 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   // weights are then re-fetched from L2 for every tile
   a.TM = a.Nt <= 64 ? 4 : 2;
   while (a.TM > 1 && (a.ntiles + a.TM - 1) / a.TM * a.NB < sm_count()) a.TM >>= 1;
+  // Wide single-block layers whose whole weight block fits next to three input stages (the last two transposed
+  // convolutions: K = 64 / 128, 256 GEMM columns) keep the weights RESIDENT and take one tile per work item: two
+  // accumulator sets then fit in TMEM and the epilogue — 256 columns per pixel for K = 64, the pacing item — overlaps
+  // the next tile's loads and MMAs (with TM = 2 the single accumulator set serialised load -> MMA -> epilogue).
+  {
+    const int64_t kc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16), it = Cin / kc * ntaps;
+    static const bool allow = [] { const char *e = getenv("MVPNET_B200_CONVG_RESIDENT"); return !(e && e[0] == '0'); }();
+    a.resident = allow && a.NB == 1 && a.Nt > 128 && it <= tcc::G_MAX_STAGES &&
+                 (size_t)it * kc * a.Nt * 4 + 2 * (size_t)kc * 512 + 1024 + Cout * 4 <= tc::SMEM_CAP;
+    if (a.resident) a.TM = 1;
+  }
   a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
   a.ngroups = (a.ntiles + a.TM - 1) / a.TM;
   a.tmem_cols = 32;
@@ -433,14 +495,17 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   // channels per stage: as many as keep three input stages (TM tiles x KC channels x 512 B) + three weight stages
   // (KC x Nt x 4 B) in shared memory — every stage costs the issuer a barrier round trip
   a.KC = 64;
-  while (a.KC > 16 && (Cin % a.KC != 0 || 3 * ((size_t)a.TM * a.KC * 512 + (size_t)a.KC * a.Nt * 4) + 1024 + Cout * 4 > tc::SMEM_CAP)) a.KC >>= 1;
+  if (a.resident) a.KC = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  while (!a.resident && a.KC > 16 && (Cin % a.KC != 0 || 3 * ((size_t)a.TM * a.KC * 512 + (size_t)a.KC * a.Nt * 4) + 1024 + Cout * 4 > tc::SMEM_CAP)) a.KC >>= 1;
   a.nchunks = (int)(Cin / a.KC);
   if (int rc = tcc::make_plane_map_g(&a.mh, x, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
   if (int rc = tcc::make_plane_map_g(&a.ml, (const __nv_bfloat16 *)x + Np_in * Cin * Hi * Wi, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
   const size_t a_stage = (size_t)a.TM * a.KC * 512, b_stage = (size_t)a.KC * a.Nt * 4;
   a.astages = a.stages = tcc::G_MAX_STAGES;
+  if (a.resident) a.stages = a.nchunks * ntaps;
   auto smem_of = [&]() { return a.astages * a_stage + a.stages * b_stage + 512 + (size_t)a.Cout * 4; };
   while (smem_of() > tc::SMEM_CAP && (a.astages > 2 || a.stages > 2)) {
+    if (a.resident) { --a.astages; continue; }
     if (a.astages >= a.stages && a.astages > 2) --a.astages; else if (a.stages > 2) --a.stages; else --a.astages;
   }
   const size_t smem = smem_of();

@@ -102,13 +102,13 @@ __device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns)
         : "memory");
-    if (!ok && ++spins > (1u << 22)) __trap();
+    if (!ok && ++spins > (1u << 20)) __trap();
   } while (!ok);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -188,6 +188,14 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
 // ---- operand packing ---------------------------------------------------------------------------
 // two fp32 values -> packed bf16 hi pair and packed bf16 lo pair (lo = rn(v - hi)), 5 instructions per pair:
 // one packing convert, two integer ops to re-expand hi, one packed fp32 subtract (FADD2), one packing convert
+// one 32-byte store (STG.256): a thread that owns 32 contiguous bytes must write them with ONE instruction — two 16-byte
+// stores reach L2 as two half-written sectors each, and the sector-write rate of L2 is what bounds a store-heavy epilogue
+__device__ __forceinline__ void st_global_256(void *p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t &h, uint32_t &l) {
   const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
   h = *reinterpret_cast<const uint32_t *>(&hh);
@@ -542,7 +550,13 @@ tc_fused_mlp_kernel(const BuildArgs a, const Chain m, float *__restrict__ out, l
               const long long pid = tile * ROWS + row;
               if (pid < a.rows_out) {
                 float *op = out + pid * m.out_channels + c * 16;
-                if ((m.out_channels & 3) == 0) {             // rows are 16-byte aligned: 128-bit stores
+                if ((m.out_channels & 7) == 0) {             // rows are 32-byte aligned: 256-bit stores (whole L2 sectors)
+#pragma unroll
+                  for (int q = 0; q < 2; ++q)
+                    if (c * 16 + 8 * q < m.out_channels)
+                      st_global_256(op + 8 * q, make_uint4(__float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3])),
+                                    make_uint4(__float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7])));
+                } else if ((m.out_channels & 3) == 0) {      // rows are 16-byte aligned: 128-bit stores
 #pragma unroll
                   for (int q = 0; q < 4; ++q)
                     if (c * 16 + 4 * q < m.out_channels)
@@ -916,6 +930,8 @@ extern "C" int mvp_tc_fused_feature_propagation(const float *sparse_feat, int64_
   MVP_REQUIRE(sparse_feat && idx && dist2 && out && (skip || Cd == 0), MVP_ERR_NULL, "tc_fused_feature_propagation: null pointer");
   MVP_REQUIRE((((uintptr_t)sparse_feat | (uintptr_t)skip) & 15) == 0, MVP_ERR_INVALID_ARG,
               "tc_fused_feature_propagation: features must be 16-byte aligned");
+  MVP_REQUIRE(((uintptr_t)out & 31) == 0 || (chain->out_channels & 7) != 0, MVP_ERR_INVALID_ARG,
+              "tc_fused_feature_propagation: the output must be 32-byte aligned (256-bit stores)");
   BuildArgs a = {};
   a.rows_out = B * Nd; a.feat_channels = (int)Cs; a.feat = sparse_feat; a.nbr = idx; a.dist = dist2; a.skip = skip;
   a.skip_channels = (int)Cd; a.n_src = Ns; a.n_out = Nd; a.k = 3; a.eps = eps;

@@ -53,6 +53,12 @@ def test_conv3x3_matches_float64(n, h, w, c1, c2, cout, res, relu):
                           nhwc_out=True)
     err = (got_f.double() - want).abs().max().item() / scale
     assert err < 2e-5, err
+    # row-split output (what the fused FeatureAggregation gathers): bf16 (hi, lo) planes, pixel-major rows
+    got_r = net2d.conv3x3(P(x1), packed, bias, x2=None if x2 is None else P(x2), residual=None if r is None else P(r), relu=relu,
+                          nhwc_out=2)
+    assert got_r.dtype == torch.bfloat16 and tuple(got_r.shape) == (2, n, h, w, cout)
+    err = (got_r[0].double() + got_r[1].double() - want).abs().max().item() / scale
+    assert err < 2e-5, err
 
 
 def test_conv3x3_errors():
