@@ -638,7 +638,7 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
     int best_tm = 1;
     for (int tm = a.TM; tm >= 1; tm >>= 1) {
       const long long works = (a.ntiles + tm - 1) / tm * a.NB, span = (works + sm_count() - 1) / sm_count() * tm;
-      if (best < 0 || span < best) { best = span; best_tm = tm; }
+      if (best < 0 || span * 100 < best * 97) { best = span; best_tm = tm; }   // a smaller TM must buy > 3 %: it multiplies the weight traffic
     }
     a.TM = best_tm;
     a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;

@@ -533,7 +533,7 @@ at::Tensor merge_planar(const at::Tensor planar, int64_t N, int64_t H, int64_t W
 // x1 (C1 channels) [+ x2 (C2 channels)] split-planar, packed weights, bias (Cout), optional split-planar residual
 // -> split-planar (N,H,W,Cout), or fp32 NHWC when nhwc_out
 at::Tensor tc_conv3x3(const at::Tensor x1, int64_t C1, const c10::optional<at::Tensor> x2, int64_t C2, int64_t N, int64_t H, int64_t W,
-                      const at::Tensor w_packed, const at::Tensor bias, const c10::optional<at::Tensor> residual, bool relu, int64_t out_mode) {
+                      const at::Tensor w_packed, const at::Tensor bias, const c10::optional<at::Tensor> residual, bool relu, int64_t out_mode, bool pair) {
   // out_mode 0: split-planar; 1: fp32 NHWC; 2: row-split (2, N, H, W, Cout) bf16 (hi plane, lo plane)
   CHECK_INPUT(x1); CHECK_INPUT(w_packed); CHECK_INPUT(bias); CHECK_F32(bias);
   const auto Cout = bias.size(0);
@@ -556,18 +556,20 @@ at::Tensor tc_conv3x3(const at::Tensor x1, int64_t C1, const c10::optional<at::T
               "tc_conv3x3: packed weights have the wrong size for ", C1 + C2, " -> ", Cout, " channels");
   c10::cuda::CUDAGuard guard(x1.device());
   at::Tensor out;
+  // pair: weights packed with half the block width, CTA-pair kernel (mvp_tc_conv3x3_pair)
+  auto conv = pair ? mvp_tc_conv3x3_pair : mvp_tc_conv3x3;
   if (out_mode == 1) {
     out = at::empty({N, H, W, Cout}, x1.options().dtype(at::kFloat));
-    check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
+    check_rc(conv(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
                             nullptr, out.data_ptr<float>(), nullptr, cur_stream()));
   } else if (out_mode == 2) {
     out = at::empty({2, N, H, W, Cout}, x1.options());
-    check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
+    check_rc(conv(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
                             nullptr, nullptr, out.data_ptr(), cur_stream()));
   } else {
     // an odd image count leaves a partner-less image in the last pair of a pair-interleaved tensor: keep it zero
     out = (H <= 8 && (N & 1)) ? at::zeros({mvp_planar_elems(N, H, W, Cout)}, x1.options()) : at::empty({mvp_planar_elems(N, H, W, Cout)}, x1.options());
-    check_rc(mvp_tc_conv3x3(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
+    check_rc(conv(x1.data_ptr(), C1, p2, C2, N, H, W, w_packed.data_ptr(), bias.data_ptr<float>(), Cout, pr, relu ? 1 : 0,
                             out.data_ptr(), nullptr, nullptr, cur_stream()));
   }
   return out;
@@ -825,6 +827,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   fz.def("tc2_set_abstraction", &tc2_set_abstraction, "pre-split gather (cp.async, swizzled operand) + MLP (tcgen05, TMEM activations) + max");
   fz.def("tc2_feature_aggregation", &tc2_feature_aggregation, "pre-split pixel gather + relation + MLP (tcgen05, TMEM activations) + reduce over k");
   fz.def("tc_conv3x3", &tc_conv3x3, "3x3 conv on split-planar activations, tcgen05 bf16 hi/lo x3 (+bias, residual, ReLU)");
+  fz.def("tc_conv3x3_pair_supported", [](int64_t cout, int64_t h) { return mvp_tc_conv3x3_pair_supported(cout, h) != 0; }, "CTA-pair 3x3 kernel usable for this layer");
   fz.def("tc_conv3x3_nt", &mvp_tc_conv3x3_nt, "output-channel block width of the packed 3x3 weights");
   fz.def("tc_conv_general", &tc_conv_general, "tap-staged conv / 2x2 transposed conv on split-planar activations (tcgen05)");
   fz.def("unfold_stem", &unfold_stem, "fp32 NCHW image -> row-unfolded split-planar (32 channels) for the 7x7 stem");

@@ -51,12 +51,27 @@ def _nt(cout):
     return cout if cout <= 256 else 256
 
 
+class PackedConv3x3:
+    """Packed weights of one 3x3 convolution: `full` for mvp_tc_conv3x3 (block width Nt), `half` for the CTA-pair kernel
+    mvp_tc_conv3x3_pair (block width Nt / 2; only where some image height can use it: Nt <= 128)."""
+    __slots__ = ('full', 'half', 'cout')
+
+    def __init__(self, full, half, cout):
+        self.full, self.half, self.cout = full, half, cout
+
+    def cuda(self):
+        return PackedConv3x3(self.full.cuda(), None if self.half is None else self.half.cuda(), self.cout)
+
+
 def pack_conv3x3(weight, bias):
-    """weight (Cout, Cin, 3, 3), bias (Cout) -> (packed, fp32 bias) for mvp_tc_conv3x3 (tap = ky*3 + kx)."""
+    """weight (Cout, Cin, 3, 3), bias (Cout) -> (PackedConv3x3, fp32 bias) for mvp_tc_conv3x3[_pair] (tap = ky*3 + kx)."""
     cout, cin = weight.shape[0], weight.shape[1]
     assert weight.shape[2:] == (3, 3)
-    nt = int(load_ext().fused_cuda.tc_conv3x3_nt(cout))              # the kernel's block width is part of the layout
-    return pack_taps(weight.reshape(cout, cin, 9), nt), bias.float().contiguous()
+    fz = load_ext().fused_cuda
+    nt = int(fz.tc_conv3x3_nt(cout))              # the kernel's block width is part of the layout
+    w9 = weight.reshape(cout, cin, 9)
+    half = pack_taps(w9, nt // 2) if fz.tc_conv3x3_pair_supported(cout, 16) else None
+    return PackedConv3x3(pack_taps(w9, nt), half, cout), bias.float().contiguous()
 
 
 def pack_conv_taps(weight, bias):
@@ -110,16 +125,19 @@ def _stage(name):
     return engine._stage(name)
 
 
-def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=0):
+def conv3x3(x1, packed, bias, x2=None, residual=None, relu=True, nhwc_out=0, pair=None):
     """x1 [, x2]: Planar inputs (concatenated along channels); residual: Planar or None.
-    Returns a Planar; nhwc_out=1: an fp32 (N, H, W, Cout) tensor; nhwc_out=2: row-split (2, N, H, W, Cout) bf16 (hi, lo planes)."""
+    Returns a Planar; nhwc_out=1: an fp32 (N, H, W, Cout) tensor; nhwc_out=2: row-split (2, N, H, W, Cout) bf16 (hi, lo planes).
+    pair: None = the CTA-pair kernel where it applies (narrow layers), False = always the single-CTA kernel."""
     with _stage('net_2d/conv3x3'):
-        return _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out)
+        return _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out, pair)
 
 
-def _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out):
-    out = load_ext().fused_cuda.tc_conv3x3(x1.data, x1.c, None if x2 is None else x2.data, 0 if x2 is None else x2.c,
-                                           x1.n, x1.h, x1.w, packed, bias, None if residual is None else residual.data, relu, int(nhwc_out))
+def _conv3x3(x1, packed, bias, x2, residual, relu, nhwc_out, pair=None):
+    fz = load_ext().fused_cuda
+    pair = pair is not False and packed.half is not None and fz.tc_conv3x3_pair_supported(packed.cout, x1.h)
+    out = fz.tc_conv3x3(x1.data, x1.c, None if x2 is None else x2.data, 0 if x2 is None else x2.c, x1.n, x1.h, x1.w,
+                        packed.half if pair else packed.full, bias, None if residual is None else residual.data, relu, int(nhwc_out), pair)
     return out if nhwc_out else Planar(out, x1.n, x1.h, x1.w, bias.numel())
 
 

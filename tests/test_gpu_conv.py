@@ -29,6 +29,9 @@ def ref_conv(x1, x2, w, b, res, relu):
     (2, 30, 37, 16, 0, 16, False, False),      # ragged everything, no activation: signed outputs
     (1, 5, 3, 32, 16, 48, True, False),
     (7, 8, 8, 16, 0, 32, False, True),
+    (1, 16, 8, 16, 0, 64, False, True),        # a single tile: the peer CTA of the pair has none
+    (3, 40, 24, 32, 0, 96, True, True),        # 27 tiles: ragged last pair item, 96-column block
+    (5, 17, 9, 16, 16, 32, False, False),
 ])
 def test_conv3x3_matches_float64(n, h, w, c1, c2, cout, res, relu):
     from mvpnet_b200 import net2d
@@ -53,6 +56,9 @@ def test_conv3x3_matches_float64(n, h, w, c1, c2, cout, res, relu):
                           nhwc_out=True)
     err = (got_f.double() - want).abs().max().item() / scale
     assert err < 2e-5, err
+    # the CTA-pair kernel (narrow layers) and the single-CTA kernel issue the same products in the same order: bit-identical
+    got_s = net2d.conv3x3(P(x1), packed, bias, x2=None if x2 is None else P(x2), residual=None if r is None else P(r), relu=relu, pair=False)
+    assert torch.equal(got_s.data, got_p.data)
     # row-split output (what the fused FeatureAggregation gathers): bf16 (hi, lo) planes, pixel-major rows
     got_r = net2d.conv3x3(P(x1), packed, bias, x2=None if x2 is None else P(x2), residual=None if r is None else P(r), relu=relu,
                           nhwc_out=2)

@@ -19,8 +19,8 @@ def conv3x3_nt(cout):
     return min(cout, 256)            # mvp_tc_conv3x3_nt
 
 
-def unpack_conv3x3(packed, cin, cout):
-    hi, lo = unpack_taps(packed, cin, cout, 9, conv3x3_nt(cout))
+def unpack_conv3x3(packed, cin, cout, nt=None):
+    hi, lo = unpack_taps(packed, cin, cout, 9, nt or conv3x3_nt(cout))
     return hi.reshape(cout, cin, 3, 3), lo.reshape(cout, cin, 3, 3)
 
 
@@ -62,6 +62,7 @@ def emulated_general(x, mode, stride, dy, dx, ho, wo, packed, bias, relu):
 def test_pack_round_trip(monkeypatch):
     class _F:
         tc_conv3x3_nt = staticmethod(conv3x3_nt)
+        tc_conv3x3_pair_supported = staticmethod(lambda cout, h: conv3x3_nt(cout) <= 128 and h > 8)
 
     class _E:
         fused_cuda = _F
@@ -70,10 +71,15 @@ def test_pack_round_trip(monkeypatch):
     for cin, cout in [(64, 64), (128, 64), (256, 512), (512, 256)]:
         w = torch.randn(cout, cin, 3, 3)
         packed, b = net2d.pack_conv3x3(w, torch.zeros(cout))
-        assert packed.numel() == cin * cout * 9 * 4
-        hi, lo = unpack_conv3x3(packed, cin, cout)
+        assert packed.full.numel() == cin * cout * 9 * 4
+        hi, lo = unpack_conv3x3(packed.full, cin, cout)
         assert torch.equal(hi, w.bfloat16().float())
         assert (hi + lo - w).abs().max() < 2 ** -16 * w.abs().max()
+        # the CTA-pair packing (narrow layers): the same values in blocks of half the width
+        assert (packed.half is not None) == (cout <= 128)
+        if packed.half is not None:
+            hi2, lo2 = unpack_conv3x3(packed.half, cin, cout, nt=conv3x3_nt(cout) // 2)
+            assert torch.equal(hi2, hi) and torch.equal(lo2, lo)
 
 
 def test_plan_matches_module_features(monkeypatch):
@@ -99,7 +105,11 @@ def test_plan_matches_module_features(monkeypatch):
             return p.reshape(n, h, w, c).clone()
 
         @staticmethod
-        def tc_conv3x3(x1, c1, x2, c2, n, h, w, packed, bias, residual, relu, nhwc_out):
+        def tc_conv3x3_pair_supported(cout, h):
+            return False
+
+        @staticmethod
+        def tc_conv3x3(x1, c1, x2, c2, n, h, w, packed, bias, residual, relu, nhwc_out, pair):
             cout = bias.numel()
             y = emulated_conv(x1.reshape(n, h, w, c1), None if x2 is None else x2.reshape(n, h, w, c2), packed, bias,
                               None if residual is None else residual.reshape(n, h, w, cout), relu)
