@@ -430,8 +430,9 @@ static int make_weight_map(CUtensorMap *m, const void *wp, int64_t bytes, int ro
 // block width mvp_tc_conv3x3_nt(Cout) / 2 (each CTA of a pair streams its own half block).
 extern "C" int mvp_tc_conv3x3_pair_supported(int64_t Cout, int64_t H) {
   static const bool allow = [] { const char *e = getenv("MVPNET_B200_CONV_PAIR"); return !(e && e[0] == '0'); }();
+  static const int64_t max_nt = [] { const char *e = getenv("MVPNET_B200_CONV_PAIR_NT"); const int64_t v = e ? atoll(e) : 0; return v >= 32 ? v : (int64_t)128; }();
   const int64_t nt = mvp_tc_conv3x3_nt(Cout);
-  return allow && nt <= 128 && nt % 32 == 0 && Cout % nt == 0 && H > 8;
+  return allow && nt <= max_nt && nt % 32 == 0 && Cout % nt == 0 && H > 8;
 }
 
 extern "C" int mvp_tc_conv3x3_pair(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,

@@ -343,25 +343,34 @@ tc_convg_kernel(const __grid_constant__ ConvGArgs a) {
 // seven row taps (dy = -3..3, dx = 0) over this tensor (unet_resnet34.py:16-21 encoder0).
 __global__ void __launch_bounds__(256)
 unfold_stem_kernel(const float *__restrict__ img, int N, int H, int W, __nv_bfloat16 *__restrict__ dst, long long plane) {
-  const long long total = (long long)N * 4 * H * W;
+  // thread = pixel (n, y, x), x fastest: 21 coalesced loads (3 channel planes x 7 consecutive columns), all four slabs
+  // written by the same thread (each slab plane is contiguous along x: 16-byte stores of consecutive lanes)
+  const long long total = (long long)N * H * W;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int x = (int)(i % W);
-    long long r = i / W;
-    const int y = (int)(r % H); r /= H;
-    const int c8 = (int)(r % 4);
-    const int n = (int)(r / 4);
-    float v[8];
+    const long long r = i / W;
+    const int y = (int)(r % H), n = (int)(r / H);
+    float v[32];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ch = c8 * 8 + e, kx = ch / 3, c = ch - kx * 3, xs = x + kx - 3;
-      v[e] = (ch < 21 && xs >= 0 && xs < W) ? __ldg(img + (((size_t)n * 3 + c) * H + y) * W + xs) : 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float *row = img + (((size_t)n * 3 + c) * H + y) * W;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int xs = x + kx - 3;
+        v[kx * 3 + c] = (xs >= 0 && xs < W) ? __ldg(row + xs) : 0.f;
+      }
     }
-    uint32_t h[4], l[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
-    const size_t o = planar_off(n, c8, y, x, 4, H, W, 0);
-    *reinterpret_cast<uint4 *>(dst + o) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4 *>(dst + plane + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    for (int e = 21; e < 32; ++e) v[e] = 0.f;
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_pair(v[c8 * 8 + 2 * q], v[c8 * 8 + 2 * q + 1], h[q], l[q]);
+      const size_t o = planar_off(n, c8, y, x, 4, H, W, 0);
+      *reinterpret_cast<uint4 *>(dst + o) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4 *>(dst + plane + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
   }
 }
 
@@ -532,7 +541,7 @@ extern "C" int mvp_unfold_stem(const float *image_nchw, int64_t N, int64_t H, in
   MVP_REQUIRE(N >= 0 && H > 8 && W > 0, MVP_ERR_INVALID_ARG, "unfold_stem: bad sizes (H must exceed 8)");
   if (N == 0) return 0;
   MVP_REQUIRE(image_nchw && planar32, MVP_ERR_NULL, "unfold_stem: null pointer");
-  const long long total = N * 4 * H * W;
+  const long long total = N * H * W;
   const unsigned grid = (unsigned)((total + 255) / 256 < (long long)sm_count() * 16 ? (total + 255) / 256 : (long long)sm_count() * 16);
   tcc::unfold_stem_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(image_nchw, (int)N, (int)H, (int)W, (__nv_bfloat16 *)planar32, N * 32 * H * W);
   return launch_status("unfold_stem");

@@ -10,7 +10,7 @@ import json
 import subprocess
 import sys
 
-FAMILIES = {'net_2d/conv3x3': 'tc_conv3x3_kernel', 'net_2d/conv_general': 'tc_convg_kernel', 'fused_sa_fa_tc2': 'tc2_kernel', 'fused_mlp_tc': 'tc_fused_mlp_kernel'}
+FAMILIES = {'net_2d/conv3x3': 'tc_conv3x3_', 'net_2d/conv_general': 'tc_convg_kernel', 'fused_sa_fa_tc2': 'tc2_kernel', 'fused_mlp_tc': 'tc_fused_mlp_kernel'}
 
 
 def to_mb(v, unit):

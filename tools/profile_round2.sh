@@ -19,7 +19,7 @@ ncu -i /tmp/full_${tag}.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.cs
 python tools/ncu_summary.py gpurun_out/full_${tag}_raw.csv > gpurun_out/ncu_full_${tag}.md 2>&1
 python tools/ncu_traffic.py gpurun_out/full_${tag}_raw.csv > gpurun_out/ncu_traffic_${tag}.json 2>&1
 cat gpurun_out/ncu_traffic_${tag}.json
-timeout 600 ncu --set full --clock-control none -k regex:"unproject_kernel|kp_query|fps_regs|pg_ball_query|ball_query_kernel|group_points|knn3|interpolate|dl_gather|transpose_kernel|seg_" -c 40 \
+MVPNET_OPS_ONCE=1 timeout 600 ncu --set full --clock-control none -k regex:"unproject_kernel|kp_query|fps_regs|pg_ball_query|group_points|pg_knn3|interpolate|dl_gather|dl_fill|dl_count|transpose_kernel|seg_" -c 40 \
    -o /tmp/ops_${tag} python tools/ops_prof.py > gpurun_out/ncu_ops_${tag}.log 2>&1
 ncu -i /tmp/ops_${tag}.ncu-rep --page raw --csv > gpurun_out/ops_${tag}_raw.csv 2>/dev/null
 python tools/ncu_summary.py gpurun_out/ops_${tag}_raw.csv > gpurun_out/ncu_ops_${tag}.md 2>&1
