@@ -39,26 +39,60 @@ NUM_POINTS, NUM_VIEWS, H, W, NUM_CLASSES, KNN = 8192, 5, 120, 160, 20, 3
 METRIC = 'chunks/sec MVPNet fwd (8192 pts, 5 views 160x120)'
 
 
+NUMA_NOTE = None
+
+
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        a, _, b = part.strip().partition('-')
+        if a.isdigit():
+            cpus.update(range(int(a), int(b if b.isdigit() else a) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa(local_rank):
-    """Best effort: pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
-    allocated (first-touch places the pages there).  With 8 ranks on one box every rank otherwise pins ~40 MB per step on
-    whatever node the launcher started it on (e2e scaling 0.83 at N = 8 with device scaling 0.96)."""
+    """Best effort: pin this process to the CPUs next to its GPU BEFORE any pinned host buffer is allocated (first touch
+    places the pages there).  With 8 ranks on one box every rank otherwise pins ~40 MB per step on whatever node the
+    launcher started it on (e2e scaling 0.83 at N = 8 with device scaling 0.96).  Sources, in order: the GPU's
+    sysfs numa_node, then the 'CPU Affinity' column of `nvidia-smi topo -m` (virtualised boxes report numa_node = -1).
+    What was found is kept in NUMA_NOTE and printed in the JSON line."""
+    global NUMA_NOTE
+    import re
+    allowed = os.sched_getaffinity(0)
     try:
         bus = subprocess.run(['nvidia-smi', '-i', str(local_rank), '--query-gpu=pci.bus_id', '--format=csv,noheader'],
                              capture_output=True, text=True, timeout=10).stdout.strip().lower()
         if len(bus.split(':')[0]) == 8:
             bus = bus[4:]
         node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read())
-        if node < 0:
+        if node >= 0:
+            cpus = _cpulist(open('/sys/devices/system/node/node%d/cpulist' % node).read()) & allowed
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                NUMA_NOTE = 'sysfs numa_node %d, %d of %d allowed cpus' % (node, len(cpus), len(allowed))
+                return node
+            NUMA_NOTE = 'sysfs numa_node %d has no cpu this process may use (%d allowed)' % (node, len(allowed))
             return None
-        cpus = set()
-        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
-            a, _, b = part.partition('-')
-            cpus.update(range(int(a), int(b or a) + 1))
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        note = 'sysfs numa_node = %d for %s' % (node, bus)
+    except Exception as e:
+        note = 'sysfs lookup failed: %s' % type(e).__name__
+    try:
+        topo = subprocess.run(['nvidia-smi', 'topo', '-m'], capture_output=True, text=True, timeout=20).stdout
+        lines = [re.sub(r'\x1b\[[0-9;]*m', '', ln) for ln in topo.splitlines()]
+        head = next(ln for ln in lines if 'CPU Affinity' in ln).split('\t')
+        col = [h.strip() for h in head].index('CPU Affinity')
+        row = next(ln for ln in lines if ln.split('\t')[0].strip() == 'GPU%d' % local_rank).split('\t')
+        cpus = _cpulist(row[col]) & allowed
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            NUMA_NOTE = note + '; nvidia-smi topo CPU affinity %s -> %d of %d allowed cpus' % (row[col].strip(), len(cpus), len(allowed))
+            numa_col = [h.strip() for h in head].index('NUMA Affinity') if 'NUMA Affinity' in [h.strip() for h in head] else -1
+            return int(row[numa_col].strip()) if numa_col >= 0 and row[numa_col].strip().isdigit() else -1
+        NUMA_NOTE = note + '; nvidia-smi topo CPU affinity "%s" does not narrow the %d allowed cpus' % (row[col].strip(), len(allowed))
+    except Exception as e:
+        NUMA_NOTE = note + '; nvidia-smi topo lookup failed: %s' % type(e).__name__
+    return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -608,8 +642,12 @@ def main():
     last = {}
     e2e_mode = {'name': ''}
 
+    submit_s = []
+
     def step_e2e():
+        t0 = time.perf_counter()
         last['out'], last['ev'] = pipe['p'].submit(host)
+        submit_s.append(time.perf_counter() - t0)
 
     def step_e2e_serial():     # the same copies on the compute stream, one after the other
         logit = step_device(to_device(host))
@@ -705,7 +743,9 @@ def main():
         pipe['p'] = engine.PipelinedForward(fwd, host, device, prepare=prepare, depth=2)
         for _ in range(2):
             step_e2e()
+        del submit_s[:]
         ms_e2e = timed(step_e2e, args.steps, drain=lambda: torch.cuda.current_stream().wait_event(last['ev']))
+        e2e_mode['host_submit_ms'] = {'mean': round(1e3 * float(np.mean(submit_s)), 3), 'max': round(1e3 * float(np.max(submit_s)), 3)}
         # the pipelined path returns what the direct call returns (same inputs every step)
         if not torch.allclose(last['out'], step_device(dev).cpu(), rtol=0, atol=1e-5):
             raise RuntimeError('pipelined result differs from the direct forward')
@@ -803,9 +843,9 @@ def main():
     bq_group = mine.get('ball_query1', 0) + mine.get('set_abstraction1', 0)
     line = {'metric': METRIC, 'value': value, 'unit': 'chunks/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': DTYPE, 'data': 'synthetic', 'config': config, 'launch_mode': graphed['note'], 'numa_node': numa_node, 'clocks': clocks,
+            'dtype': DTYPE, 'data': 'synthetic', 'config': config, 'launch_mode': graphed['note'], 'numa_node': numa_node, 'numa_note': NUMA_NOTE, 'host_cpus': len(os.sched_getaffinity(0)), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'chunks/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'ms_per_step': ms_e2e / args.steps, 'mode': e2e_mode['name']},
+                    'ms_per_step': ms_e2e / args.steps, 'mode': e2e_mode['name'], 'host_submit_ms': e2e_mode.get('host_submit_ms')},
             'gpu_launches': launches_mine * args.steps,
             'gpu_launches_note': '%d kernels of this package + %d ATen kernels per step, counted from CUPTI activity records of one eager step '
                                  '(torch.profiler); the timed steps replay the same launches from CUDA graphs' % (launches_mine, launches_all - launches_mine),
