@@ -685,9 +685,36 @@ def main():
     lane_graphs, lane_streams = [], []
     if not args.no_cuda_graph and not args.no_extras:
         try:
-            graphed['fn'] = engine.GraphedForward(model, batch_of(dev))
+            execs = min(4, max(1, int(os.environ.get('MVPNET_B200_BENCH_EXECS', '1'))))
+
+            class RotatingGraph:
+                """`execs` instantiations of the same captured forward used in turn: the host can enqueue the next launch
+                of a lane while the previous one (another executable graph) is still running."""
+
+                def __init__(self, graphs):
+                    self.graphs, self.n, self.cur = graphs, 0, graphs[0]
+
+                def load(self, batch):
+                    self.cur = self.graphs[self.n % len(self.graphs)]
+                    self.n += 1
+                    self.cur.load(batch)
+
+                def replay(self):
+                    return self.cur.replay()
+
+                def __call__(self, batch):
+                    self.load(batch)
+                    return self.replay()
+
+            def new_lane():
+                gs = [engine.GraphedForward(model, batch_of(dev)) for _ in range(execs)]
+                return gs[0] if execs == 1 else RotatingGraph(gs)
+
+            graphed['fn'] = new_lane()
             graphed['note'] = 'one CUDA graph replay per step (2D network + both streams captured)'
-            lane_graphs = [graphed['fn']] + [engine.GraphedForward(model, batch_of(dev)) for _ in range(lanes - 1)]
+            lane_graphs = [graphed['fn']] + [new_lane() for _ in range(lanes - 1)]
+            if execs > 1:
+                graphed['note'] += '; %d executable graphs per lane used in turn' % execs
             lane_streams = [torch.cuda.Stream(device) for _ in range(lanes)]
             if lanes > 1:
                 graphed['note'] += '; consecutive steps alternate between %d graphs on %d streams' % (lanes, lanes)

@@ -290,12 +290,11 @@ kp_qscatter_kernel(const double *__restrict__ query, int nq, const KpGrid *__res
 
 // 4 CTAs per SM: 64 registers without spills (98 registers unbounded = 2 CTAs; the kernel is latency-bound, ncu round 1: 30 % warps active)
 template <int KMAX>
-__global__ void __launch_bounds__(256, 4)
-kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ grids, const int *__restrict__ cells,
-                const KpRec *__restrict__ sorted, const int *__restrict__ order, int nq, int P, int k,
-                int blocks_per_cloud, int64_t *__restrict__ index, double *__restrict__ dist2) {
-  const int b = blockIdx.x / blocks_per_cloud;
-  const int slot = (blockIdx.x % blocks_per_cloud) * 8 + (threadIdx.x >> 5);
+__device__ __forceinline__ void kp_query_block(int vblock, const double *__restrict__ query, const KpGrid *__restrict__ grids, const int *__restrict__ cells,
+                                               const KpRec *__restrict__ sorted, const int *__restrict__ order, int nq, int P, int k,
+                                               int blocks_per_cloud, int64_t *__restrict__ index, double *__restrict__ dist2) {
+  const int b = vblock / blocks_per_cloud;
+  const int slot = (vblock % blocks_per_cloud) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (slot >= nq) return;  // warp-uniform
   const int q = order ? __ldg(order + (size_t)b * nq + slot) : slot;
@@ -425,6 +424,20 @@ kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ gri
   }
 }
 
+// Warps are independent (one query each, no block-level synchronisation): the kernel walks virtual blocks with a grid
+// stride, so the launch can be sized.  Default: every block its own CTA (4 resident per SM = the whole register file).
+// MVPNET_B200_KP_CTAS_PER_SM = n > 0 launches n CTAs per SM instead: with n = 1 the search takes a quarter of the
+// registers and can stay resident NEXT TO a persistent convolution CTA of the 2D network (it is not needed before the
+// 2D network ends), instead of displacing it.
+template <int KMAX>
+__global__ void __launch_bounds__(256, 4)
+kp_query_kernel(const double *__restrict__ query, const KpGrid *__restrict__ grids, const int *__restrict__ cells,
+                const KpRec *__restrict__ sorted, const int *__restrict__ order, int nq, int P, int k,
+                int blocks_per_cloud, int total_blocks, int64_t *__restrict__ index, double *__restrict__ dist2) {
+  for (int vb = blockIdx.x; vb < total_blocks; vb += gridDim.x)
+    kp_query_block<KMAX>(vb, query, grids, cells, sorted, order, nq, P, k, blocks_per_cloud, index, dist2);
+}
+
 static inline size_t kp_align(size_t x) { return (x + 255) / 256 * 256; }
 
 }  // namespace mvp
@@ -484,9 +497,11 @@ extern "C" int mvp_knn_pixels(const double *query, const double *pix_xyz, const 
   const int bpc = (int)((nq + 7) / 8);
   const int64_t grid = B * bpc;
   MVP_REQUIRE(grid < (1LL << 31), MVP_ERR_UNSUPPORTED, "knn_pixels: too many queries");
+  static const int per_sm = [] { const char *e = getenv("MVPNET_B200_KP_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
+  const int64_t launch = per_sm > 0 && (int64_t)per_sm * sm_count() < grid ? (int64_t)per_sm * sm_count() : grid;
   if (k <= 3)
-    kp_query_kernel<3><<<(unsigned)grid, 256, 0, stream>>>(query, grids, cells, sorted, ord, (int)nq, (int)P, (int)k, bpc, index, dist2);
+    kp_query_kernel<3><<<(unsigned)launch, 256, 0, stream>>>(query, grids, cells, sorted, ord, (int)nq, (int)P, (int)k, bpc, (int)grid, index, dist2);
   else
-    kp_query_kernel<8><<<(unsigned)grid, 256, 0, stream>>>(query, grids, cells, sorted, ord, (int)nq, (int)P, (int)k, bpc, index, dist2);
+    kp_query_kernel<8><<<(unsigned)launch, 256, 0, stream>>>(query, grids, cells, sorted, ord, (int)nq, (int)P, (int)k, bpc, (int)grid, index, dist2);
   return launch_status("knn_pixels");
 }

@@ -502,6 +502,16 @@ merge_planar_kernel(const __nv_bfloat16 *__restrict__ src, long long plane, int 
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------
+// Shared-memory budget of the convolution kernels (MVPNET_B200_CONV_SMEM_KB overrides).  Lowering it to 224 KB lets one
+// small CTA of a geometry-stream kernel (the pixel k-NN with MVPNET_B200_KP_CTAS_PER_SM=1: no shared memory beyond the
+// 1 KB the system reserves per CTA, a quarter of the register file) stay resident next to a persistent convolution CTA.
+// Measured (round 2): no gain — the step was 1.8 % slower with the search spread under the convolutions than with the
+// search taking the whole GPU for 1 ms — so the default is the full 227 KB.
+static size_t conv_smem_cap() {
+  static const size_t cap = [] { const char *e = getenv("MVPNET_B200_CONV_SMEM_KB"); const long v = e ? atol(e) : 0; return (size_t)((v >= 96 && v <= 227) ? v : 227) * 1024; }();
+  return cap;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -672,12 +682,12 @@ extern "C" int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_
     }
   }
   auto smem_of = [&]() { return (size_t)a.asets * a.TM * tcc::SLOT_BYTES + (size_t)a.stages * a.tps * 64 * a.Nt + 512 + (size_t)a.Cout * 4; };
-  while (a.stages > 3 && smem_of() > tc::SMEM_CAP) --a.stages;
-  while (a.asets > 2 && smem_of() > tc::SMEM_CAP) --a.asets;
-  while (a.stages > 2 && smem_of() > tc::SMEM_CAP) --a.stages;
-  if (smem_of() > tc::SMEM_CAP && a.tps > 1) { a.tps = a.tps == 9 ? 3 : 1; a.stages = tcc::MAX_STAGES; while (a.stages > 2 && smem_of() > tc::SMEM_CAP) --a.stages; }
+  while (a.stages > 3 && smem_of() > tcc::conv_smem_cap()) --a.stages;
+  while (a.asets > 2 && smem_of() > tcc::conv_smem_cap()) --a.asets;
+  while (a.stages > 2 && smem_of() > tcc::conv_smem_cap()) --a.stages;
+  if (smem_of() > tcc::conv_smem_cap() && a.tps > 1) { a.tps = a.tps == 9 ? 3 : 1; a.stages = tcc::MAX_STAGES; while (a.stages > 2 && smem_of() > tcc::conv_smem_cap()) --a.stages; }
   const size_t smem = smem_of();
-  MVP_REQUIRE(smem <= tc::SMEM_CAP, MVP_ERR_UNSUPPORTED, "tc_conv3x3: shared memory budget exceeded");
+  MVP_REQUIRE(smem <= tcc::conv_smem_cap(), MVP_ERR_UNSUPPORTED, "tc_conv3x3: shared memory budget exceeded");
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_conv3x3: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;

@@ -499,11 +499,11 @@ extern "C" int mvp_tc_conv3x3_pair(const void *x1, int64_t C1, const void *x2, i
     if (tp && (atoi(tp) == 1 || atoi(tp) == 3 || atoi(tp) == 9)) a.tps = atoi(tp);
   }
   auto smem_of = [&]() { return (size_t)a.asets * a.TM * tcc::SLOT_BYTES + (size_t)a.stages * a.tps * 32 * a.Nt + 512 + (size_t)a.Cout * 4; };
-  while (a.stages > 3 && smem_of() > tc::SMEM_CAP) --a.stages;
-  while (a.asets > 2 && smem_of() > tc::SMEM_CAP) --a.asets;
-  while (a.stages > 2 && smem_of() > tc::SMEM_CAP) --a.stages;
+  while (a.stages > 3 && smem_of() > tcc::conv_smem_cap()) --a.stages;
+  while (a.asets > 2 && smem_of() > tcc::conv_smem_cap()) --a.asets;
+  while (a.stages > 2 && smem_of() > tcc::conv_smem_cap()) --a.stages;
   const size_t smem = smem_of();
-  MVP_REQUIRE(smem <= tc::SMEM_CAP, MVP_ERR_UNSUPPORTED, "tc_conv3x3_pair: shared memory budget exceeded");
+  MVP_REQUIRE(smem <= tcc::conv_smem_cap(), MVP_ERR_UNSUPPORTED, "tc_conv3x3_pair: shared memory budget exceeded");
   CUtensorMap wmap;
   if (int rc = tcc::make_weight_map(&wmap, w_packed_half, (C1 + C2) * Cout * 9 * 4, (32 * a.Nt) >> 7)) return rc;
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

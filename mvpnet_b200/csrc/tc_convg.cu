@@ -494,7 +494,7 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
     const int64_t kc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16), it = Cin / kc * ntaps;
     static const bool allow = [] { const char *e = getenv("MVPNET_B200_CONVG_RESIDENT"); return !(e && e[0] == '0'); }();
     a.resident = allow && a.NB == 1 && a.Nt > 128 && it <= tcc::G_MAX_STAGES &&
-                 (size_t)it * kc * a.Nt * 4 + 2 * (size_t)kc * 512 + 1024 + Cout * 4 <= tc::SMEM_CAP;
+                 (size_t)it * kc * a.Nt * 4 + 2 * (size_t)kc * 512 + 1024 + Cout * 4 <= tcc::conv_smem_cap();
     if (a.resident) a.TM = 1;
   }
   a.nacc = 2 * a.TM * a.Nt <= 512 ? 2 : 1;
@@ -505,7 +505,7 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   // (KC x Nt x 4 B) in shared memory — every stage costs the issuer a barrier round trip
   a.KC = 64;
   if (a.resident) a.KC = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
-  while (!a.resident && a.KC > 16 && (Cin % a.KC != 0 || 3 * ((size_t)a.TM * a.KC * 512 + (size_t)a.KC * a.Nt * 4) + 1024 + Cout * 4 > tc::SMEM_CAP)) a.KC >>= 1;
+  while (!a.resident && a.KC > 16 && (Cin % a.KC != 0 || 3 * ((size_t)a.TM * a.KC * 512 + (size_t)a.KC * a.Nt * 4) + 1024 + Cout * 4 > tcc::conv_smem_cap())) a.KC >>= 1;
   a.nchunks = (int)(Cin / a.KC);
   if (int rc = tcc::make_plane_map_g(&a.mh, x, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
   if (int rc = tcc::make_plane_map_g(&a.ml, (const __nv_bfloat16 *)x + Np_in * Cin * Hi * Wi, N, Hi, Wi, Cin, a.in_pair, stride, a.KC / 8)) return rc;
@@ -513,12 +513,12 @@ extern "C" int mvp_tc_conv_general(const void *x, int64_t Cin, int64_t N, int64_
   a.astages = a.stages = tcc::G_MAX_STAGES;
   if (a.resident) a.stages = a.nchunks * ntaps;
   auto smem_of = [&]() { return a.astages * a_stage + a.stages * b_stage + 512 + (size_t)a.Cout * 4; };
-  while (smem_of() > tc::SMEM_CAP && (a.astages > 2 || a.stages > 2)) {
+  while (smem_of() > tcc::conv_smem_cap() && (a.astages > 2 || a.stages > 2)) {
     if (a.resident) { --a.astages; continue; }
     if (a.astages >= a.stages && a.astages > 2) --a.astages; else if (a.stages > 2) --a.stages; else --a.astages;
   }
   const size_t smem = smem_of();
-  MVP_REQUIRE(smem <= tc::SMEM_CAP, MVP_ERR_UNSUPPORTED, "tc_conv_general: shared memory budget exceeded");
+  MVP_REQUIRE(smem <= tcc::conv_smem_cap(), MVP_ERR_UNSUPPORTED, "tc_conv_general: shared memory budget exceeded");
   cudaError_t e = cudaFuncSetAttribute(tcc::tc_convg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tc_conv_general: smem attribute (%zu B): %s", smem, cudaGetErrorString(e)); return (int)e; }
   const long long nworks = a.ngroups * a.NB;
