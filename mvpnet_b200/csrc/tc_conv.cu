@@ -158,6 +158,128 @@ __device__ __forceinline__ void sched_retire(unsigned int *counter) {
   __syncwarp();
 }
 
+// ---- epilogue of one work item (shared by the single-CTA and the CTA-pair kernel) ------------------------------------
+// thread = TMEM lane = pixel of a tile; the two warps of a lane quarter take alternate 16-column chunks.  The (tile, chunk)
+// items of a work item form one software pipeline: the residual of item i + 1 is in flight while item i is finished, and the
+// first item's residual is requested BEFORE the accumulator barrier.
+struct EpiThread {
+  int g, xx;                // tile row / column of this thread's pixel
+  uint32_t t_lane;          // TMEM address of this thread's lane (column 0)
+  int C8o, c0, cpt, pair;
+  size_t slab_stride;       // elements between slabs of one image
+};
+
+__device__ __forceinline__ EpiThread epi_thread(const ConvArgs &a, int warp, int lane, uint32_t tmem_base) {
+  EpiThread e;
+  const int quarter = warp & 3, half = warp >> 2, row = quarter * 32 + lane;
+  e.g = row >> 3; e.xx = row & 7;
+  e.t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  e.C8o = a.Cout >> 3;
+  e.pair = a.ipt == 2;
+  e.slab_stride = (size_t)a.H * a.W * 8 * (e.pair ? 2 : 1);
+  e.c0 = half * 16;
+  e.cpt = (a.Nt - e.c0 + 31) / 32;                         // this thread's chunks per tile
+  return e;
+}
+
+// tiles [tile0, tile0 + nt) of output block nb, accumulators in set `set`; waits for `bar_full` (phase `parity`) itself
+__device__ __forceinline__ void epilogue_tiles(const ConvArgs &a, const EpiThread &e, int nb, long long tile0, int nt, uint32_t set,
+                                               const float *s_bias, uint32_t bar_full, uint32_t parity) {
+  const int g = e.g, xx = e.xx, pair = e.pair, c0 = e.c0, cpt = e.cpt;
+  const size_t slab_stride = e.slab_stride;
+  struct Item { size_t pbase, fbase; bool ok; };
+  auto locate = [&](long long tile) {
+    Item r;
+    const TileCoord tc_ = tile_coord(a, tile);
+    const int img = pair ? tc_.n + (g & 1) : tc_.n;
+    const int y = pair ? (g >> 1) : tc_.y0 + g;
+    const int x = tc_.x0 + xx;
+    r.ok = img < a.N && y < a.H && x < a.W && !(a.dbg & 2);
+    r.pbase = r.ok ? planar_off(img, nb * (a.Nt >> 3), y, x, e.C8o, a.H, a.W, pair) : 0;
+    r.fbase = r.ok ? (((size_t)img * a.H + y) * a.W + x) * a.Cout + (size_t)nb * a.Nt : 0;
+    return r;
+  };
+  auto load_res = [&](const Item &p, int c, uint4 (&rh)[2], uint4 (&rl)[2]) {
+    if (a.res != nullptr && p.ok) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const size_t o = p.pbase + (size_t)((c >> 3) + s) * slab_stride;
+        rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + o));
+        rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + o));
+      }
+    }
+  };
+  const float *bias_s = s_bias + nb * a.Nt;
+  Item cur = locate(nt > 0 ? tile0 : 0);
+  uint4 rh[2], rl[2];
+  if (cpt > 0 && nt > 0) load_res(cur, c0, rh, rl);
+  mbar_wait(bar_full, parity);
+  tc_fence_after();
+  for (int t = 0; t < nt && cpt > 0; ++t) {
+    const uint32_t t_acc = e.t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
+    Item nxt = cur;
+    if (t + 1 < nt) nxt = locate(tile0 + t + 1);
+    uint32_t rn[16];
+    tmem_ld16_issue(t_acc + (uint32_t)c0, rn);
+    for (int c = c0; c < a.Nt; c += 32) {
+      float v[16];
+      tmem_ld_wait(rn);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
+      if (c + 32 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 32), rn);
+      const float4 *bp = reinterpret_cast<const float4 *>(bias_s + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bq = bp[q];
+        v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+      }
+      if (a.res != nullptr) {
+        if (cur.ok) {
+          float r0[8], r1[8];
+          unpack8(rh[0], rl[0], r0);
+          unpack8(rh[1], rl[1], r1);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { v[q] += r0[q]; v[8 + q] += r1[q]; }
+        }
+        if (c + 32 < a.Nt) load_res(cur, c + 32, rh, rl);          // next item: same tile, next chunk ...
+        else if (t + 1 < nt) load_res(nxt, c0, rh, rl);              // ... or the first chunk of the next tile
+      }
+      if (cur.ok) {
+        if (a.relu) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+        if (a.out_p != nullptr) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_pair(v[8 * s + 2 * q], v[8 * s + 2 * q + 1], h[q], l[q]);
+            const size_t o = cur.pbase + (size_t)((c >> 3) + s) * slab_stride;
+            *reinterpret_cast<uint4 *>(a.out_p + o) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(a.out_p + a.plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        if (a.out_f != nullptr) {
+          float *op = a.out_f + cur.fbase + c;
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            st_global_256(op + 8 * q, make_uint4(__float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3])),
+                          make_uint4(__float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7])));
+        }
+        if (a.out_rh != nullptr) {   // what the fused FeatureAggregation gathers: pixel-major rows, already split
+          uint32_t h[8], l[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
+          st_global_256(a.out_rh + cur.fbase + c, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
+          st_global_256(a.out_rl + cur.fbase + c, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
+        }
+      }
+    }
+    cur = nxt;
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -196,38 +318,8 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
   const int pair = a.ipt == 2;
 
   if (warp < EPI_WARPS) {
-    // =========================== epilogue: thread = TMEM lane = pixel; the two warps of a lane quarter take
-    //                             alternate 16-column chunks ==================================================
-    // The (tile, chunk) items of a work item form one software pipeline: the residual of item i + 1 is in flight
-    // while item i is finished, and the first item's residual is requested BEFORE the accumulator barrier.
-    const int quarter = warp & 3, half = warp >> 2;
-    const int row = quarter * 32 + lane, g = row >> 3, xx = row & 7;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int C8o = a.Cout >> 3;
-    const size_t slab_stride = (size_t)a.H * a.W * 8 * (pair ? 2 : 1);           // elements between slabs of one image
-    const int c0 = half * 16, cpt = (a.Nt - c0 + 31) / 32;                       // this thread's chunks per tile
-    struct Item { size_t pbase, fbase; bool ok; };
-    auto locate = [&](long long tile, int nb) {
-      Item r;
-      const TileCoord tc_ = tile_coord(a, tile);
-      const int img = pair ? tc_.n + (g & 1) : tc_.n;
-      const int y = pair ? (g >> 1) : tc_.y0 + g;
-      const int x = tc_.x0 + xx;
-      r.ok = img < a.N && y < a.H && x < a.W && !(a.dbg & 2);
-      r.pbase = r.ok ? planar_off(img, nb * (a.Nt >> 3), y, x, C8o, a.H, a.W, pair) : 0;
-      r.fbase = r.ok ? (((size_t)img * a.H + y) * a.W + x) * a.Cout + (size_t)nb * a.Nt : 0;
-      return r;
-    };
-    auto load_res = [&](const Item &p, int c, uint4 (&rh)[2], uint4 (&rl)[2]) {
-      if (a.res != nullptr && p.ok) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const size_t o = p.pbase + (size_t)((c >> 3) + s) * slab_stride;
-          rh[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + o));
-          rl[s] = __ldg(reinterpret_cast<const uint4 *>(a.res + a.plane_out + o));
-        }
-      }
-    };
+    // =========================== epilogue (epilogue_tiles above) ======================================================
+    const EpiThread e = epi_thread(a, warp, lane, tmem_base);
     for (uint32_t it = 0;; ++it) {
       const int w = sched_consume(it, s_ring, bar_sfull, bar_sempty);
       if (w >= nworks) break;
@@ -236,75 +328,7 @@ tc_conv3x3_kernel(const __grid_constant__ ConvArgs a) {
       const uint32_t set = it % NA;
       const long long left = a.ntiles - group * a.TM;
       const int nt = left < a.TM ? (int)left : a.TM;
-      const float *bias_s = s_bias + nb * a.Nt;
-      Item cur = locate(group * a.TM, nb);
-      uint4 rh[2], rl[2];
-      if (cpt > 0) load_res(cur, c0, rh, rl);
-      mbar_wait(bar_accfull + 8 * set, (it / NA) & 1u);
-      tc_fence_after();
-      for (int t = 0; t < nt && cpt > 0; ++t) {
-        const uint32_t t_acc = t_lane + (uint32_t)((set * a.TM + t) * a.Nt);
-        Item nxt = cur;
-        if (t + 1 < nt) nxt = locate(group * a.TM + t + 1, nb);
-        uint32_t rn[16];
-        tmem_ld16_issue(t_acc + (uint32_t)c0, rn);
-        for (int c = c0; c < a.Nt; c += 32) {
-          float v[16];
-          tmem_ld_wait(rn);
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = __uint_as_float(rn[q]);
-          if (c + 32 < a.Nt) tmem_ld16_issue(t_acc + (uint32_t)(c + 32), rn);
-          const float4 *bp = reinterpret_cast<const float4 *>(bias_s + c);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bq = bp[q];
-            v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
-          }
-          if (a.res != nullptr) {
-            if (cur.ok) {
-              float r0[8], r1[8];
-              unpack8(rh[0], rl[0], r0);
-              unpack8(rh[1], rl[1], r1);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) { v[q] += r0[q]; v[8 + q] += r1[q]; }
-            }
-            if (c + 32 < a.Nt) load_res(cur, c + 32, rh, rl);          // next item: same tile, next chunk ...
-            else if (t + 1 < nt) load_res(nxt, c0, rh, rl);              // ... or the first chunk of the next tile
-          }
-          if (cur.ok) {
-            if (a.relu) {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q], 0.f);
-            }
-            if (a.out_p != nullptr) {
-#pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) split_pair(v[8 * s + 2 * q], v[8 * s + 2 * q + 1], h[q], l[q]);
-                const size_t o = cur.pbase + (size_t)((c >> 3) + s) * slab_stride;
-                *reinterpret_cast<uint4 *>(a.out_p + o) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4 *>(a.out_p + a.plane_out + o) = make_uint4(l[0], l[1], l[2], l[3]);
-              }
-            }
-            if (a.out_f != nullptr) {
-              float *op = a.out_f + cur.fbase + c;
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-                st_global_256(op + 8 * q, make_uint4(__float_as_uint(v[8 * q]), __float_as_uint(v[8 * q + 1]), __float_as_uint(v[8 * q + 2]), __float_as_uint(v[8 * q + 3])),
-                              make_uint4(__float_as_uint(v[8 * q + 4]), __float_as_uint(v[8 * q + 5]), __float_as_uint(v[8 * q + 6]), __float_as_uint(v[8 * q + 7])));
-            }
-            if (a.out_rh != nullptr) {   // what the fused FeatureAggregation gathers: pixel-major rows, already split
-              uint32_t h[8], l[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
-              st_global_256(a.out_rh + cur.fbase + c, make_uint4(h[0], h[1], h[2], h[3]), make_uint4(h[4], h[5], h[6], h[7]));
-              st_global_256(a.out_rl + cur.fbase + c, make_uint4(l[0], l[1], l[2], l[3]), make_uint4(l[4], l[5], l[6], l[7]));
-            }
-          }
-        }
-        cur = nxt;
-      }
+      epilogue_tiles(a, e, nb, group * a.TM, nt, set, s_bias, bar_accfull + 8 * set, (it / NA) & 1u);
       tc_fence_before();
       mbar_arrive(bar_accempty + 8 * set);
     }
