@@ -851,7 +851,7 @@ def main():
     t_fused = sum(mine[k] for k in fused)
     gf_fused = sum(flops_pc[k] for k in fused) * cpg
     n_launch = launches.get(top, 1)
-    roof = {'kernel': top + (' (tc_conv3x3_pair_kernel [cta_group::2, Cout <= 128] + tc_conv3x3_kernel, %d launches per step: every 3x3/stride-1 convolution of the UNet)' % n_launch if top == 'net_2d/conv3x3' else ''),
+    roof = {'kernel': top + (' (tc_conv3x3_pair_kernel [cta_group::2, every level above 8 image rows] + tc_conv3x3_kernel [the 8 x 10 level], %d launches per step: every 3x3/stride-1 convolution of the UNet)' % n_launch if top == 'net_2d/conv3x3' else ''),
             'bound': 'hbm' if top == 'feature_aggregation' else 'tensor', 'peak_source': peak_src,
             'launches_per_step': n_launch, 'ms_per_launch': mine[top] / n_launch,
             'traffic': traffic_mb.get(top, NCU_TRAFFIC_MB.get(top)),

@@ -286,8 +286,8 @@ int64_t mvp_planar_elems(int64_t N, int64_t H, int64_t W, int64_t C);
 int mvp_tc_conv3x3(const void *x1, int64_t C1, const void *x2, int64_t C2, int64_t N, int64_t H, int64_t W,
                    const void *w_packed, const float *bias, int64_t Cout, const void *residual, int relu,
                    void *out_planar, float *out_nhwc, void *out_rows, mvp_stream_t stream);
-/* CTA-pair variant (csrc/tc_conv_pair.cu: tcgen05.mma.cta_group::2, two SMs per 256-pixel tile pair) for output blocks
- * of <= 128 channels on images of more than 8 rows — mvp_tc_conv3x3_pair_supported(Cout, H).  Same arguments and
+/* CTA-pair variant (csrc/tc_conv_pair.cu: tcgen05.mma.cta_group::2, two SMs per 256-pixel tile pair) for images of more
+ * than 8 rows (output blocks of 32..256 channels) — mvp_tc_conv3x3_pair_supported(Cout, H).  Same arguments and
  * bit-identical results; the weights are packed with block width mvp_tc_conv3x3_nt(Cout) / 2 (each CTA of a pair streams
  * its own half block): [2 * Cout/Nt][Cin/16][tap][hi|lo][2][Nt/2][8], 128-byte aligned. */
 int mvp_tc_conv3x3_pair_supported(int64_t Cout, int64_t H);

@@ -1,4 +1,4 @@
-// CTA-pair variant of the 3x3 convolution of tc_conv.cu for the narrow layers (Cout <= 128): tcgen05.mma.cta_group::2.
+// CTA-pair variant of the 3x3 convolution of tc_conv.cu (every level above 8 image rows): tcgen05.mma.cta_group::2.
 //
 // Why: an SS-mode MMA reads its A tile (128 pixels x 16 channels = 4 KB) and its B tile (16 x Nt x 2 B) from shared
 // memory every time it is issued.  At Nt = 64 that is 6 KB per 32 tensor-pipe cycles = 192 B/cycle against the 128
@@ -6,7 +6,10 @@
 // network's 3x3 time) ran at ~58 cycles per MMA instead of 32 (profiles/r2_conv_dbg.txt).  Two CTAs on the two SMs of
 // a TPC issue ONE M = 256 MMA: each SM reads its own 128 pixels and only HALF of the weights (Nt/2 columns, the
 // hardware exchanges the halves), 5 KB per SM per MMA at Nt = 64, and each CTA fetches only half of every weight
-// stage from L2.
+// stage from L2.  The 256-channel layers are not operand-fetch bound, but with half the weight stream per CTA they can
+// take ONE tile per CTA and work item (TM = 1) without flooding L2, so that two accumulator sets fit tensor memory and
+// their epilogue (residual add included) overlaps the next item's MMAs: +2-3 % on the whole step (MVPNET_B200_CONV_PAIR_NT=128
+// keeps them on the single-CTA kernel).
 //
 // Structure (same roles, rings and arithmetic as tc_conv3x3_kernel — results are bit-identical):
 //   * cluster of 2 CTAs; a work item is 2 x TM tiles, CTA r takes tiles [r*TM, r*TM + TM) of it
@@ -331,11 +334,11 @@ static int make_weight_map(CUtensorMap *m, const void *wp, int64_t bytes, int ro
 }  // namespace tcc
 }  // namespace mvp
 
-// The pair kernel serves output blocks of <= 128 channels on images of more than 8 rows.  Its weights are packed with
+// The pair kernel serves images of more than 8 rows (output blocks of 32..256 channels, multiples of 32).  Its weights are packed with
 // block width mvp_tc_conv3x3_nt(Cout) / 2 (each CTA of a pair streams its own half block).
 extern "C" int mvp_tc_conv3x3_pair_supported(int64_t Cout, int64_t H) {
   static const bool allow = [] { const char *e = getenv("MVPNET_B200_CONV_PAIR"); return !(e && e[0] == '0'); }();
-  static const int64_t max_nt = [] { const char *e = getenv("MVPNET_B200_CONV_PAIR_NT"); const int64_t v = e ? atoll(e) : 0; return v >= 32 ? v : (int64_t)128; }();
+  static const int64_t max_nt = [] { const char *e = getenv("MVPNET_B200_CONV_PAIR_NT"); const int64_t v = e ? atoll(e) : 0; return v >= 32 ? v : (int64_t)256; }();
   const int64_t nt = mvp_tc_conv3x3_nt(Cout);
   return allow && nt <= max_nt && nt % 32 == 0 && Cout % nt == 0 && H > 8;
 }
@@ -347,7 +350,7 @@ extern "C" int mvp_tc_conv3x3_pair(const void *x1, int64_t C1, const void *x2, i
   MVP_REQUIRE(N >= 0 && H > 0 && W > 0, MVP_ERR_INVALID_ARG, "tc_conv3x3_pair: bad sizes");
   MVP_REQUIRE(C1 > 0 && C1 % 16 == 0 && C2 >= 0 && C2 % 16 == 0, MVP_ERR_UNSUPPORTED, "tc_conv3x3_pair: input channels must be multiples of 16");
   MVP_REQUIRE(Cout > 0 && mvp_tc_conv3x3_pair_supported(Cout, H), MVP_ERR_UNSUPPORTED,
-              "tc_conv3x3_pair: needs output blocks of 32..128 channels (multiples of 32) and H > 8 (mvp_tc_conv3x3_pair_supported)");
+              "tc_conv3x3_pair: needs output blocks of 32..256 channels (multiples of 32) and H > 8 (mvp_tc_conv3x3_pair_supported)");
   MVP_REQUIRE(N * H * W < (1LL << 31), MVP_ERR_UNSUPPORTED, "tc_conv3x3_pair: more than 2^31 pixels");
   if (N == 0) return 0;
   MVP_REQUIRE(x1 && w_packed_half && bias && (out_planar || out_nhwc || out_rows) && (x2 || C2 == 0), MVP_ERR_NULL, "tc_conv3x3_pair: null pointer");
@@ -373,7 +376,7 @@ extern "C" int mvp_tc_conv3x3_pair(const void *x1, int64_t C1, const void *x2, i
   a.ntiles = N * a.TX * a.TY;
   const int pairs = sm_count() / 2;
   // tiles per CTA and work item: the largest TM with the smallest makespan over the CTA pairs (see mvp_tc_conv3x3)
-  a.TM = a.Nt <= 64 ? 4 : 2;
+  a.TM = a.Nt <= 64 ? 4 : (a.Nt <= 128 ? 2 : 1);     // 256 columns: one tile per CTA, so that two accumulator sets fit tensor memory
   {
     long long best = -1;
     int best_tm = 1;

@@ -53,7 +53,7 @@ def _nt(cout):
 
 class PackedConv3x3:
     """Packed weights of one 3x3 convolution: `full` for mvp_tc_conv3x3 (block width Nt), `half` for the CTA-pair kernel
-    mvp_tc_conv3x3_pair (block width Nt / 2; only where some image height can use it: Nt <= 128)."""
+    mvp_tc_conv3x3_pair (block width Nt / 2; used wherever the image has more than 8 rows)."""
     __slots__ = ('full', 'half', 'cout')
 
     def __init__(self, full, half, cout):

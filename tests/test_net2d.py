@@ -62,7 +62,7 @@ def emulated_general(x, mode, stride, dy, dx, ho, wo, packed, bias, relu):
 def test_pack_round_trip(monkeypatch):
     class _F:
         tc_conv3x3_nt = staticmethod(conv3x3_nt)
-        tc_conv3x3_pair_supported = staticmethod(lambda cout, h: conv3x3_nt(cout) <= 128 and h > 8)
+        tc_conv3x3_pair_supported = staticmethod(lambda cout, h: h > 8)
 
     class _E:
         fused_cuda = _F
@@ -76,7 +76,7 @@ def test_pack_round_trip(monkeypatch):
         assert torch.equal(hi, w.bfloat16().float())
         assert (hi + lo - w).abs().max() < 2 ** -16 * w.abs().max()
         # the CTA-pair packing (narrow layers): the same values in blocks of half the width
-        assert (packed.half is not None) == (cout <= 128)
+        assert packed.half is not None
         if packed.half is not None:
             hi2, lo2 = unpack_conv3x3(packed.half, cin, cout, nt=conv3x3_nt(cout) // 2)
             assert torch.equal(hi2, hi) and torch.equal(lo2, lo)
