@@ -733,27 +733,6 @@ extern "C" int64_t mvp_fps_workspace_bytes(int64_t B, int64_t N, int64_t D, int6
   return B * N * (dtype == MVP_F64 ? 8 : 4);
 }
 
-namespace mvp {
-// One CTA per cloud holds a whole SM (registers) for ~1 ms while the 2D network runs CTA PAIRS (clusters of 2 = the two
-// SMs of a TPC, tc_conv_pair.cu) on the other stream: 32 clouds spread over 32 TPCs would block 32 pairs, half-used.
-// Launched as clusters of 2 the clouds fill 16 TPCs completely instead.  No cooperation between the two CTAs.
-template <typename... KArgs, typename... Args>
-static void launch_tpc_pairs(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args... args) {
-  static const bool pairs = [] { const char *e = getenv("MVPNET_B200_FPS_TPC_PAIRS"); return !(e && e[0] == '0'); }();
-  if (pairs && grid >= 2 && grid % 2 == 0) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...) == cudaSuccess) return;
-    cudaGetLastError();              // e.g. no TPC with both SMs available to this context: plain launch below
-  }
-  kernel<<<grid, block, smem, stream>>>(KArgs(args)...);
-}
-}  // namespace mvp
-
 extern "C" int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int64_t M, int dtype,
                        int64_t *index, void *workspace, mvp_stream_t stream_) {
   using namespace mvp;
@@ -793,7 +772,7 @@ extern "C" int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int6
       threads16 = (threads16 + 31) / 32 * 32;
       const size_t smem16 = (size_t)N * 3 * sizeof(float) + (size_t)N * sizeof(unsigned short);
       cudaFuncSetAttribute(fps_regs_kernel<16, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
-      launch_tpc_pairs(fps_regs_kernel<16, true, 512>, (unsigned)B, (unsigned)threads16, smem16, stream, (const float *)points, index, (int)N, (int)M, lg);
+      fps_regs_kernel<16, true, 512><<<(unsigned)B, threads16, smem16, stream>>>((const float *)points, index, (int)N, (int)M, lg);
       return launch_status("fps");
     }
     // plain kernel: T must be a multiple of the reference BLOCK (= 1 << lg, <= 512) for the p-order tie rule (see the kernel)
@@ -806,7 +785,7 @@ extern "C" int mvp_fps(const void *points, int64_t B, int64_t N, int64_t D, int6
 #define MVP_FPS_LAUNCH(P, BK)                                                                          \
   do {                                                                                                 \
     cudaFuncSetAttribute(fps_regs_kernel<P, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    launch_tpc_pairs(fps_regs_kernel<P, BK>, (unsigned)B, (unsigned)threads, smem, stream, p, index, (int)N, (int)M, lg);     \
+    fps_regs_kernel<P, BK><<<(unsigned)B, threads, smem, stream>>>(p, index, (int)N, (int)M, lg);     \
   } while (0)
     switch (ppt) {
       case 1: MVP_FPS_LAUNCH(1, false); break;
