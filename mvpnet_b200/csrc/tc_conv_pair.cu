@@ -37,8 +37,17 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// arrive on a barrier of either CTA.  `_cl`: release at CLUSTER scope — everything this thread wrote before (the remote
+// store of a work index) is visible to the other CTA's waiter; it costs a cluster-wide memory fence (MEMBAR), which behind
+// the output stores of an epilogue warp showed up as 6 % of the kernel's stall samples (profiles/r2_conv_pair_lines.txt).
+// The plain form (default semantics, CTA scope, what CUTLASS' ClusterBarrier::arrive(cta_id) emits) is enough where
+// nothing written by generic-proxy stores is handed over: releasing an accumulator set (ordered by
+// tcgen05.fence::before_thread_sync) or a ring slot that was only read.
 __device__ __forceinline__ void mbar_arrive_cl(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
@@ -115,7 +124,7 @@ __device__ __forceinline__ int sched_consume2(uint32_t k, volatile int *ring, ui
   mbar_wait_cl(bar_full + 8 * slot, (k / SCHED_DEPTH) & 1u);
   const int w = ring[slot];
   __syncwarp();
-  if (elect_one()) mbar_arrive_cl(mapa(bar_empty + 8 * slot, 0));
+  if (elect_one()) mbar_arrive_remote(mapa(bar_empty + 8 * slot, 0));
   __syncwarp();
   return w;
 }
@@ -176,7 +185,7 @@ tc_conv3x3_pair_kernel(const __grid_constant__ ConvArgs a, const __grid_constant
       epilogue_tiles(a, e, nb, (group * 2 + rank) * a.TM, tiles_of(group, rank), set, s_bias, bar_accfull + 8 * set, (it / NA) & 1u);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cl(accempty_leader + 8 * set);      // one arrival per epilogue warp of either CTA
+      if (lane == 0) mbar_arrive_remote(accempty_leader + 8 * set);  // one arrival per epilogue warp of either CTA
     }
   } else if (warp == EPI_WARPS) {
     // =========================== MMA issuer: the leader CTA only ======================================================
